@@ -1,0 +1,197 @@
+/*
+ * b200pnm.h -- C-ABI of libb200pnm.so: the B200-native transport-solve path
+ * of OpenPNM (assembly -> boundary conditions -> sources -> Jacobi-PCG ->
+ * Picard loop -> rate), hand-written CUDA for sm_100a.
+ *
+ * This is the drop-in boundary.  The reference (pure Python, /root/reference,
+ * citations below are file:line under it) has no FFI of its own; the entry
+ * points here are what a ctypes/cffi binding inside `openpnm.solvers` and
+ * `openpnm.algorithms` would bind -- see INTEGRATION.md for that stub.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = B200_OK, <0 = error
+ *     (b200_last_error(ctx) gives the text).  No C++ exception crosses this
+ *     boundary.  Solver outcome (converged / maxiter / breakdown) is NOT an
+ *     error: it is reported through an `info` out-parameter with SciPy's
+ *     convention (0 converged, >0 = iterations done when maxiter hit,
+ *     <0 breakdown), which is what `Transport._run_special` stores into
+ *     `soln.is_converged = not bool(exit_code)` (algorithms/_transport.py:221).
+ *   - pointers are DEVICE pointers unless the name ends in `_h` (host).
+ *     Scalar out-parameters (`int64_t* nnz`, `double* f`, ...) are host.
+ *   - float data is float64; `conns`/pore lists are int64 as in the reference
+ *     (network['throat.conns']); CSR/COO indices are int32 as in SciPy.
+ *   - a context owns one device, one stream and all workspace; it is not
+ *     thread-safe (the reference calls the path from one Python thread,
+ *     GIL held: algorithms/_reactive_transport.py:196-210).
+ */
+#ifndef B200PNM_H
+#define B200PNM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_ctx b200_ctx;
+
+enum {
+  B200_OK = 0,
+  B200_ERR_CUDA = -1,          /* a CUDA runtime call failed                  */
+  B200_ERR_ARG = -2,           /* bad argument / wrong call order            */
+  B200_ERR_INDEX = -3,         /* pore index out of range in conns / COO     */
+  B200_ERR_NONFINITE = -4,     /* inf/nan in A, b or x0 (ref: "A or b contains
+                                  inf/nan values", _transport.py:253-257)     */
+  B200_ERR_TOO_LARGE = -5,     /* nnz >= 2^31 (SciPy int32 index limit)      */
+  B200_ERR_NCCL = -6,
+  B200_ERR_SINGULAR = -7       /* a row has a zero diagonal and no BC        */
+};
+
+/* which matrix an export / spmv call refers to */
+enum { B200_MAT_PURE = 0, B200_MAT_SYSTEM = 1 };
+
+/* source-term models: openpnm/models/physics/source_terms/_funcs.py
+ *   LINEAR            :73-116   r = p1*X + p2
+ *   POWER_LAW         :120-168  r = p1*X^p2 + p3
+ *   STANDARD_KINETICS :21-69    r = p1*X^p2                                 */
+enum { B200_SRC_LINEAR = 0, B200_SRC_POWER_LAW = 1, B200_SRC_STANDARD_KINETICS = 2 };
+
+/* storage the PCG picked for the Jacobi-scaled operator */
+enum { B200_FMT_NONE = 0, B200_FMT_CSR = 1, B200_FMT_DIA = 2 };
+
+/* ---------------------------------------------------------------- lifecycle */
+int b200_version(void);
+int b200_create(int device, b200_ctx** out);
+int b200_destroy(b200_ctx* ctx);
+const char* b200_last_error(b200_ctx* ctx);
+/* stream all work of this context is enqueued on (a cudaStream_t).  The host
+ * may hand in its own (e.g. torch.cuda.current_stream().cuda_stream) so that
+ * its copies and this library's kernels are ordered without extra syncs.    */
+void* b200_stream(b200_ctx* ctx);
+int b200_set_stream(b200_ctx* ctx, void* cuda_stream);
+int b200_synchronize(b200_ctx* ctx);
+
+/* ----------------------------------------------------- K1: Laplacian assembly
+ * Replaces Network.create_adjacency_matrix(weights=g, fmt='coo')
+ * (network/_network.py:265-293) + scipy.sparse.csgraph.laplacian
+ * (algorithms/_transport.py:113-114) + A.tocsr() (solvers/_scipy.py:13-14):
+ * conns (Nt,2) int64 C-order, g (Nt,) f64 -> canonical CSR of L = D - W
+ * (column-sorted, duplicate throats summed, self-loops dropped, explicit
+ * zeros kept), built without floating-point atomics: integer histogram ->
+ * exclusive scan -> fill -> per-row sort on (col, throat) -> fixed-order
+ * segmented sums.  Rows [row_begin,row_end) only (slab ownership); pass
+ * 0,Np for the whole network.  Column indices stay global.                  */
+int b200_build_laplacian(b200_ctx* ctx, const int64_t* conns, const double* g,
+                         int64_t Np, int64_t Nt, int64_t row_begin,
+                         int64_t row_end, int64_t* nnz);
+
+/* ------------------------------------------------ K2: boundary conditions
+ * Replaces Transport._build_b + _apply_BCs (_transport.py:117-121,145-169).
+ * bc_value / bc_rate: (Np,) f64 for ALL pores (global indexing), NaN = no BC;
+ * either may be NULL.  Produces the system matrix (BC rows/cols eliminated,
+ * f on BC diagonals, zeros compacted away = eliminate_zeros) and b.
+ * f = mean of the pure diagonal; for a slab, pass the global sum and count
+ * through b200_set_diag_mean() first, otherwise the local mean is used.     */
+int b200_apply_bcs(b200_ctx* ctx, const double* bc_value, const double* bc_rate,
+                   int keep_zero_diag, double* f, int64_t* nnz);
+int b200_pure_diag_sum(b200_ctx* ctx, double* sum, int64_t* count);
+int b200_set_diag_mean(b200_ctx* ctx, double f);
+
+/* ------------------------------------------------------------ generic system
+ * For solver.solve(A, b, x0) where A was assembled by the reference itself
+ * (solvers/_base.py:6-14, _transport.py:213): COO triples (unsorted, possibly
+ * duplicated; exactly what `alg.A` is) -> canonical system CSR like
+ * `A.tocsr()`.                                                              */
+int b200_load_coo(b200_ctx* ctx, const int32_t* row, const int32_t* col,
+                  const double* data, int64_t nnz_in, int64_t n, int64_t* nnz);
+int b200_load_csr(b200_ctx* ctx, const int32_t* indptr, const int32_t* indices,
+                  const double* data, int64_t n, int64_t nnz);
+int b200_set_b(b200_ctx* ctx, const double* b);
+int b200_get_b(b200_ctx* ctx, double* b);
+
+/* sizes + export (device destinations) for the bit-exact index parity tests */
+int b200_csr_shape(b200_ctx* ctx, int which, int64_t* nrows, int64_t* nnz);
+int b200_export_csr(b200_ctx* ctx, int which, int32_t* indptr, int32_t* indices,
+                    double* data);
+
+/* ----------------------------------------------------------- K3: SpMV
+ * y = M x for the pure or the system matrix (CSR, fp64/int32).  x, y (n,).
+ * `A * x` at _transport.py:159 and _reactive_transport.py:244.              */
+int b200_spmv(b200_ctx* ctx, int which, const double* x, double* y);
+
+/* ------------------------------------------------- K4: Jacobi-PCG
+ * Replaces solver.solve(A, b, x0) -> (x, exit_code) (solvers/_scipy.py:8-26).
+ * Solves system * x = b by CG on the symmetrically Jacobi-scaled operator
+ * D^-1/2 A D^-1/2 (unit diagonal; identical iterates to Jacobi-PCG in exact
+ * arithmetic).  Stops when ||b - A x||_2 <= max(rtol*||b||_2, atol) -- the
+ * rule ScipyCG uses (tol=self.tol, atol=norm(b)*tol).  x0 may be NULL
+ * (zeros) and is never written.  b200_pcg_prepare() (re)builds the scaled
+ * operator after the system matrix changed; b200_pcg() calls it if needed. */
+int b200_set_format(b200_ctx* ctx, int force_format);   /* 0 = automatic */
+int b200_pcg_prepare(b200_ctx* ctx, int force_format);
+int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol,
+             int64_t maxiter, double* x, int64_t* iters, double* relres,
+             int* info);
+int b200_pcg_format(b200_ctx* ctx, int* fmt, int* ndiags);
+
+/* ------------------------------------------- K5: sources + Picard loop
+ * Replaces ReactiveTransport.set_source bookkeeping hand-off,
+ * _update_iterative_props (_algorithm.py:69-91), _apply_sources
+ * (_reactive_transport.py:125-148), _get_residual (:234-244) and the outer
+ * loop _run_special (:150-213) including SciPy's TerminationCondition
+ * (2-norms, f_rtol AND x_rtol) and the first-iteration dx == 0 quirk
+ * (_solution.py:17-20).  mask: (n,) uint8; p1..p3: (n,) f64 (p3 may be NULL).
+ * With zero sources the loop degenerates to one linear solve (num_iter 1).  */
+int b200_clear_sources(b200_ctx* ctx);
+int b200_add_source(b200_ctx* ctx, int kind, const uint8_t* mask,
+                    const double* p1, const double* p2, const double* p3);
+int b200_picard(b200_ctx* ctx, const double* x0, double relaxation,
+                int64_t newton_maxiter, double f_rtol, double x_rtol,
+                double cg_rtol, int64_t cg_maxiter, double* x,
+                int64_t* num_iter, int* converged, int64_t* cg_iters_total,
+                int* last_info);
+
+/* ---------------------------------------------------------------- K6: rate
+ * Replaces Transport.rate (_transport.py:259-330).  Pores: net rate leaving
+ * each pore = (L_pure x)[pore]; out has k entries (mode 'single') and the
+ * caller sums for 'group'.  Throats: |g (x[c1]-x[c0])|.                     */
+int b200_rate_pores(b200_ctx* ctx, const double* x, const int64_t* pores,
+                    int64_t k, double* out);
+int b200_rate_throats(b200_ctx* ctx, const int64_t* conns, const double* g,
+                      const double* x, const int64_t* throats, int64_t k,
+                      double* out);
+
+/* ------------------------------------------------------------- statistics */
+typedef struct b200_stats {
+  int64_t n, nnz_system, cg_iters;
+  int fmt, ndiags;
+  double t_setup_ms, t_solve_ms;      /* CUDA-event times of the last pcg     */
+  double relres;
+  int64_t kernel_launches;            /* kernels launched by this ctx so far  */
+} b200_stats;
+int b200_get_stats(b200_ctx* ctx, b200_stats* out);
+
+/* --------------------------------------------------- host-buffer entry points
+ * What a ctypes binder holding numpy arrays calls; H2D/D2H copies inside.
+ * b200_solve_coo_h is the whole of `B200PCG.solve(A, b, x0)`.               */
+int b200_solve_coo_h(b200_ctx* ctx, const int32_t* row_h, const int32_t* col_h,
+                     const double* data_h, int64_t nnz_in, int64_t n,
+                     const double* b_h, const double* x0_h, double rtol,
+                     double atol, int64_t maxiter, double* x_h, int64_t* iters,
+                     double* relres, int* info);
+
+/* ------------------------------------------------------ multi-GPU (slabs)
+ * One context per rank.  The unique id is produced on rank 0 and broadcast by
+ * the host (torch.distributed); after b200_comm_init the PCG exchanges halo
+ * windows with rank-1/rank+1 and all-reduces its dot products over NCCL.
+ * The reference's only statement of this algorithm is its PETSc wrapper
+ * (row-block ownership, CG + Jacobi: solvers/_petsc.py:117-128,160).        */
+int b200_nccl_unique_id(void* id128_h);
+int b200_comm_init(b200_ctx* ctx, int nranks, int rank, const void* id128_h);
+int b200_set_slab(b200_ctx* ctx, int64_t n_global, int64_t row_begin,
+                  int64_t row_end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PNM_H */

@@ -1,0 +1,485 @@
+"""Host-side mirror of `openpnm.algorithms.{Transport, ReactiveTransport,
+StokesFlow, FickianDiffusion, OhmicConduction, FourierConduction}` whose
+assembly, boundary conditions, source linearisation, solve, Picard loop and
+`rate()` all run on the GPU through libb200pnm.so.
+
+Same method names, argument meaning and error behaviour as the reference
+(file:line under /root/reference):
+    openpnm/algorithms/_transport.py:45-74      settings, __init__
+    openpnm/algorithms/_transport.py:171-207    run
+    openpnm/algorithms/_transport.py:229-257    validators
+    openpnm/algorithms/_transport.py:259-379    rate, set_*_BC, clear_*_BCs
+    openpnm/algorithms/_algorithm.py:105-225    set_BC bookkeeping
+    openpnm/algorithms/_reactive_transport.py:43-123,246-256  sources
+    openpnm/algorithms/_stokes_flow.py:21-32 etc.  settings-only subclasses
+`network` / `phase` may be real OpenPNM objects or the containers in
+`openpnm_b200.network`.
+"""
+import logging
+
+import numpy as np
+
+from . import _lib
+from .solvers import B200PCG
+
+__all__ = ["Transport", "ReactiveTransport", "StokesFlow", "FickianDiffusion",
+           "OhmicConduction", "FourierConduction", "SolutionContainer", "SteadyStateSolution"]
+
+logger = logging.getLogger(__name__)
+
+_SRC_KINDS = {
+    "linear": (_lib.SRC_LINEAR, ("A1", "A2", None), (0.0, 0.0, 0.0)),
+    "power_law": (_lib.SRC_POWER_LAW, ("A1", "A2", "A3"), (0.0, 0.0, 0.0)),
+    "standard_kinetics": (_lib.SRC_STANDARD_KINETICS, ("prefactor", "exponent", None),
+                          (None, None, 0.0)),
+}
+
+
+class SolutionContainer(dict):
+    """openpnm/algorithms/_solution.py:10"""
+    pass
+
+
+class SteadyStateSolution(np.ndarray):
+    """openpnm/algorithms/_solution.py:15-20"""
+
+    def __new__(cls, x):
+        return np.asarray(x).view(cls)
+
+
+class Settings(dict):
+    """attribute + item access, `_update` like openpnm.utils.SettingsAttr"""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def _update(self, d):
+        self.update(dict(d))
+
+
+class Transport(dict):
+    """Steady-state linear transport on the GPU (reference: Transport)."""
+
+    _defaults = dict(quantity="", conductance="", cache=True, variable_props=set(),
+                     validate_topology=True, cg_rtol=None)
+
+    def __init__(self, network, phase, name="trans_?", **kwargs):
+        super().__init__()
+        self.network = network
+        self._phase = phase
+        self.name = name
+        self.settings = Settings(self._defaults)
+        self.settings["variable_props"] = set()
+        self.settings["phase"] = getattr(phase, "name", "phase")
+        self.settings._update(kwargs)
+        self.Np = int(network.Np)
+        self.Nt = int(network.Nt)
+        dict.__setitem__(self, "pore.all", np.ones(self.Np, dtype=bool))
+        dict.__setitem__(self, "throat.all", np.ones(self.Nt, dtype=bool))
+        dict.__setitem__(self, "pore.bc.rate", np.full(self.Np, np.nan))
+        dict.__setitem__(self, "pore.bc.value", np.full(self.Np, np.nan))
+        self.soln = {}
+        self._ctx = None
+        self._x_dev = None
+        self._cache_key = None
+        self.stats = {}
+
+    # ------------------------------------------------------------ dict rules
+    def __setitem__(self, key, value):
+        n = self.Np if key.startswith("pore.") else self.Nt if key.startswith("throat.") else None
+        if n is None:
+            raise KeyError("keys must start with 'pore.' or 'throat.'")
+        a = np.asarray(value)
+        if a.ndim == 0:
+            a = np.full(n, a[()])
+        elif a.shape[0] != n:
+            raise ValueError(f"{key}: expected length {n}")
+        dict.__setitem__(self, key, np.array(a))
+
+    def __getitem__(self, key):
+        try:
+            return dict.__getitem__(self, key)
+        except KeyError:
+            pre = key + "."
+            sub = {k[len(pre):]: v for k, v in self.items() if k.startswith(pre)}
+            if sub:
+                return sub
+            if key == "pore.source":
+                return {}          # _transport.py:76-83
+            raise KeyError(key)
+
+    @property
+    def Ps(self):
+        return np.arange(self.Np)
+
+    @property
+    def x(self):
+        """Shortcut to the solution currently stored on the algorithm."""
+        return self[self.settings["quantity"]]
+
+    @x.setter
+    def x(self, value):
+        self[self.settings["quantity"]] = value
+
+    def _parse_indices(self, indices):
+        if indices is None:
+            return np.array([], dtype=np.int64)
+        a = np.asarray(indices)
+        if a.dtype == bool:
+            a = np.flatnonzero(a)
+        return np.atleast_1d(a).astype(np.int64).ravel()
+
+    # --------------------------------------------------------------- BCs
+    def set_value_BC(self, pores=None, values=[], mode="add"):
+        self.set_BC(pores=pores, bctype="value", bcvalues=values, mode=mode)
+
+    def set_rate_BC(self, pores=None, rates=[], mode="add"):
+        self.set_BC(pores=pores, bctype="rate", bcvalues=rates, mode=mode)
+
+    def clear_value_BCs(self):
+        self.set_BC(pores=None, bctype="value", mode="remove")
+
+    def clear_rate_BCs(self):
+        self.set_BC(pores=None, bctype="rate", mode="remove")
+
+    def clear_BCs(self, bctype=[]):
+        self.set_BC(pores=None, bctype=bctype, mode="remove")
+
+    def set_BC(self, pores=None, bctype=[], bcvalues=[], mode="add"):
+        """openpnm/algorithms/_algorithm.py:105-225 (same modes and errors)."""
+        if not isinstance(mode, str):
+            for item in mode:
+                self.set_BC(pores=pores, bctype=bctype, bcvalues=bcvalues, mode=item)
+            return
+        if len(bctype) == 0:
+            bctype = list(self["pore.bc"].keys())
+        if not isinstance(bctype, str):
+            for item in bctype:
+                self.set_BC(pores=pores, bctype=item, bcvalues=bcvalues, mode=mode)
+            return
+        if mode not in ("add", "overwrite", "remove"):
+            raise Exception(f"Unsupported mode {mode}")
+        bc_types = list(self["pore.bc"].keys())
+        other_types = [t for t in bc_types if t != bctype]
+        pores = self.Ps if pores is None else self._parse_indices(pores)
+        values = np.array(bcvalues, dtype=float)
+        if values.size == 1:
+            values = np.ones(pores.size) * values.ravel()[0]
+        if values.size > 1 and values.size != pores.size:
+            raise Exception("The number of values must match the number of locations")
+        if mode == "add":
+            mask = np.ones(pores.size, dtype=bool)
+            for item in bc_types:
+                mask[~np.isnan(self[f"pore.bc.{item}"][pores])] = False
+            if not np.all(mask):
+                raise Exception("Some of the given locations already have BCs, either use "
+                                "mode='remove' first or use mode='overwrite' instead")
+            self[f"pore.bc.{bctype}"][pores[mask]] = values[mask]
+        elif mode == "overwrite":
+            self[f"pore.bc.{bctype}"][pores] = values
+            for item in other_types:
+                self[f"pore.bc.{item}"][pores] = np.nan
+        elif mode == "remove":
+            self[f"pore.bc.{bctype}"][pores] = np.nan
+
+    # -------------------------------------------------------- validators
+    def _validate_settings(self):
+        for k in ("quantity", "conductance", "phase"):
+            if self.settings.get(k) is None:
+                raise Exception(f"'{k}' hasn't been defined on this algorithm")
+
+    def _validate_topology_health(self):
+        """Every cluster must touch a BC pore (_transport.py:243-251 ->
+        topotools.is_fully_connected, topotools/_topotools.py:993-1024); host
+        graph check with scipy's C connected_components (no LIL detour)."""
+        import scipy.sparse as sprs
+        from scipy.sparse import csgraph
+        conns = np.asarray(self.network["throat.conns"])
+        bc = ~np.isnan(self["pore.bc.rate"]) | ~np.isnan(self["pore.bc.value"])
+        am = sprs.coo_matrix((np.ones(conns.shape[0], dtype=np.int8),
+                              (conns[:, 0], conns[:, 1])), shape=(self.Np, self.Np))
+        ncomp, labels = csgraph.connected_components(am, directed=False)
+        if ncomp == 1:
+            return
+        touched = np.zeros(ncomp, dtype=bool)
+        touched[labels[bc]] = True
+        if not touched.all():
+            raise Exception("Your network is clustered, making Ax = b ill-conditioned")
+
+    # ------------------------------------------------------------- solve
+    def _sources(self):
+        return []
+
+    def _conductance(self):
+        g = np.asarray(self._phase[self.settings["conductance"]], dtype=np.float64)
+        if g.shape != (self.Nt,):
+            raise Exception("Received weights are of incorrect length")
+        return g
+
+    def _assemble(self, ctx):
+        """_build_A + _build_b + _apply_BCs on the device."""
+        g = self._conductance()
+        key = (id(ctx), id(self.network), g.__array_interface__["data"][0], g.size)
+        if not (self.settings["cache"] and self._cache_key == key):
+            conns = np.asarray(self.network["throat.conns"], dtype=np.int64)
+            ctx.build_laplacian(conns, g, self.Np)
+            self._cache_key = key
+        nsrc = len(self._sources())
+        f, nnz = ctx.apply_bcs(self["pore.bc.value"], self["pore.bc.rate"],
+                               keep_zero_diag=nsrc > 0)
+        return f, nnz
+
+    def run(self, solver=None, x0=None, verbose=False):
+        """Builds A and b on the GPU, solves, stores the result in `alg.x` and
+        `alg.soln` (reference: Transport.run, _transport.py:171-207)."""
+        if solver is None:
+            solver = B200PCG()
+        if not getattr(solver, "_b200_native", False):
+            raise TypeError("openpnm_b200 algorithms need a B200PCG solver "
+                            "(there is no CPU path)")
+        self._validate_settings()
+        if self.settings["validate_topology"]:
+            self._validate_topology_health()
+        x0 = np.zeros(self.Np) if x0 is None else np.array(x0, dtype=np.float64)
+        if not np.isfinite(x0).all():
+            raise Exception("x0 contains inf/nan values")
+        self["pore.initial_guess"] = x0
+        self.soln = SolutionContainer()
+        self.soln.is_converged = False
+        ctx = solver.ctx
+        self._ctx = ctx
+        ctx.set_format(solver._fmt_code())
+        try:
+            self._assemble(ctx)
+            ctx.clear_sources()
+            for mask, kind, p1, p2, p3 in self._sources():
+                ctx.add_source(kind, mask, p1, p2, p3)
+            s = self.settings
+            cg_rtol = s["cg_rtol"] if s.get("cg_rtol") else solver.tol
+            x_dev, num_iter, conv, cg_iters, info = ctx.picard(
+                x0=x0 if np.any(x0) else None,
+                relaxation=s.get("relaxation_factor", 1.0),
+                newton_maxiter=s.get("newton_maxiter", 5000),
+                f_rtol=s.get("f_rtol", 1e-6), x_rtol=s.get("x_rtol", 1e-6),
+                cg_rtol=cg_rtol, cg_maxiter=0 if solver.maxiter is None else solver.maxiter)
+        except _lib.B200Error as e:
+            if e.code == -4:
+                raise Exception("A or b contains inf/nan values") from e
+            raise
+        self._x_dev = x_dev
+        x = x_dev.cpu().numpy()
+        self.x = x
+        q = self.settings["quantity"]
+        self.soln[q] = SteadyStateSolution(x.copy())
+        self.soln.is_converged = bool(conv)
+        self.soln.num_iter = int(num_iter)
+        self.soln.cg_iters = int(cg_iters)
+        self.soln.exit_code = int(info)
+        self.stats = ctx.stats()
+        self.soln.relres = self.stats["relres"]
+        if not conv:
+            logger.warning(f"{self.name} didn't converge after {num_iter} iterations")
+        self._post_run(x)
+
+    def _post_run(self, x):
+        pass
+
+    @property
+    def A(self):
+        """The coefficient matrix as assembled on the device (scipy CSR)."""
+        if self._ctx is None:
+            raise Exception("run() first")
+        return self._ctx.export_csr_scipy(_lib.MAT_SYSTEM)
+
+    @property
+    def b(self):
+        if self._ctx is None:
+            raise Exception("run() first")
+        return self._ctx.get_b().cpu().numpy()
+
+    def rate(self, pores=[], throats=[], mode="group"):
+        """Net rate leaving `pores` / magnitude through `throats`
+        (reference: Transport.rate, _transport.py:259-330)."""
+        pores = self._parse_indices(pores)
+        throats = self._parse_indices(throats)
+        if throats.size > 0 and pores.size > 0:
+            raise Exception("Must specify either pores or throats, not both")
+        if throats.size == 0 and pores.size == 0:
+            raise Exception("Must specify either pores or throats")
+        if self._ctx is None:
+            raise Exception("run() first")
+        x = self._x_dev if self._x_dev is not None else self.x
+        if throats.size:
+            R = self._ctx.rate_throats(x, throats).cpu().numpy()
+        else:
+            R = self._ctx.rate_pores(x, pores).cpu().numpy()
+        if mode == "group":
+            R = np.sum(R)
+        return np.array(R, ndmin=1)
+
+
+class ReactiveTransport(Transport):
+    """Steady transport with (optional) nonlinear source terms; the Picard /
+    Newton-linearised outer loop runs on the device (reference:
+    ReactiveTransport, _reactive_transport.py)."""
+
+    def __init__(self, network, phase, name="react_trans_?", **kwargs):
+        super().__init__(network=network, phase=phase, name=name, **kwargs)
+        for k, v in dict(relaxation_factor=1.0, newton_maxiter=5000, f_rtol=1e-6,
+                         x_rtol=1e-6).items():
+            self.settings.setdefault(k, v)
+
+    def set_source(self, pores, propname, mode="add"):
+        """_reactive_transport.py:70-123"""
+        if isinstance(mode, list):
+            for item in mode:
+                self.set_source(pores=pores, propname=propname, mode=item)
+            return
+        if not propname.startswith("pore."):
+            propname = "pore." + propname
+        pores = self._parse_indices(pores)
+        locs_BC = np.zeros(self.Np, dtype=bool)
+        for item in self["pore.bc"].keys():
+            locs_BC |= np.isfinite(self[f"pore.bc.{item}"])
+        if np.any(locs_BC[pores]):
+            raise Exception("BCs present in given pores, can't assign source term")
+        prop = "pore.source." + propname.split(".", 1)[1]
+        if mode == "add":
+            if prop not in self.keys():
+                self[prop] = False
+            dict.__getitem__(self, prop)[pores] = True
+        elif mode == "remove":
+            dict.__getitem__(self, prop)[pores] = False
+        elif mode == "clear":
+            self[prop] = False
+        else:
+            raise Exception(f"Unsupported mode {mode}")
+
+    def set_BC(self, pores=None, bctype=[], bcvalues=[], mode="add"):
+        """_reactive_transport.py:246-256: BCs may not land on source pores."""
+        if isinstance(mode, str) and mode != "remove" and pores is not None:
+            ps = self._parse_indices(pores)
+            for item in self["pore.source"].keys():
+                if np.any(self["pore.source." + item][ps]):
+                    raise Exception("Source term already present in given pores, "
+                                    "can't assign BCs")
+        super().set_BC(pores=pores, bctype=bctype, bcvalues=bcvalues, mode=mode)
+
+    def _model_of(self, item):
+        models = getattr(self._phase, "models", None)
+        key = "pore." + item
+        if models is None or key not in models:
+            # OpenPNM stores 'propname@domain' keys too
+            cands = [k for k in (models or {}) if k.split("@")[0] == key]
+            if not cands:
+                raise KeyError(f"no source model '{key}' on the phase")
+            key = cands[0]
+        m = models[key]
+        fn = m["model"]
+        name = fn if isinstance(fn, str) else getattr(fn, "__name__", str(fn))
+        if name not in _SRC_KINDS:
+            raise NotImplementedError(
+                f"source model '{name}' has no device kernel (linear, power_law, "
+                "standard_kinetics are implemented)")
+        return name, m
+
+    def _sources(self):
+        out = []
+        for item in self["pore.source"].keys():
+            mask = np.asarray(self["pore.source." + item], dtype=bool)
+            name, m = self._model_of(item)
+            if m.get("X", self.settings["quantity"]) != self.settings["quantity"]:
+                raise Exception("source term X must be the algorithm's quantity")
+            kind, keys, defaults = _SRC_KINDS[name]
+            ps = []
+            for k, d in zip(keys, defaults):
+                if k is None:
+                    ps.append(None)
+                    continue
+                v = m.get(k, d)
+                if isinstance(v, str):
+                    v = np.asarray(self._phase[v], dtype=np.float64)
+                ps.append(v)
+            out.append((mask, kind, ps[0], ps[1], ps[2]))
+        return out
+
+    def _post_run(self, x):
+        """Leave S1 / S2 / rate of each source on the phase at the converged x,
+        as `regenerate_models` does in the reference (_algorithm.py:89-91)."""
+        try:
+            self._phase[self.settings["quantity"]] = x
+        except Exception:
+            return
+        for item in self["pore.source"].keys():
+            name, m = self._model_of(item)
+            _, keys, defaults = _SRC_KINDS[name]
+            p = []
+            for k, d in zip(keys, defaults):
+                v = d if k is None else m.get(k, d)
+                if isinstance(v, str):
+                    v = np.asarray(self._phase[v], dtype=np.float64)
+                p.append(v)
+            with np.errstate(all="ignore"):
+                if name == "linear":
+                    S1, S2 = p[0] * np.ones_like(x), p[1] * np.ones_like(x)
+                    r = p[0] * x + p[1]
+                elif name == "power_law":
+                    r = p[0] * x ** p[1] + p[2]
+                    S1 = p[0] * p[1] * x ** (p[1] - 1)
+                    S2 = p[0] * x ** p[1] * (1 - p[1]) + p[2]
+                else:
+                    r = p[0] * x ** p[1]
+                    S1 = p[0] * p[1] * x ** (p[1] - 1)
+                    S2 = p[0] * (1 - p[1]) * x ** p[1]
+            try:
+                self._phase[f"pore.{item}.S1"] = S1
+                self._phase[f"pore.{item}.S2"] = S2
+                self._phase[f"pore.{item}.rate"] = r
+            except Exception:
+                pass
+
+
+class StokesFlow(ReactiveTransport):
+    """_stokes_flow.py:21-32"""
+
+    def __init__(self, network, phase, name="stokes_?", **kwargs):
+        super().__init__(network=network, phase=phase, name=name, **kwargs)
+        self.settings._update(dict(quantity="pore.pressure",
+                                   conductance="throat.hydraulic_conductance"))
+        self.settings._update(kwargs)
+
+
+class FickianDiffusion(ReactiveTransport):
+    """_fickian_diffusion.py:22-55"""
+
+    def __init__(self, network, phase, name="fick_?", **kwargs):
+        super().__init__(network=network, phase=phase, name=name, **kwargs)
+        self.settings._update(dict(quantity="pore.concentration",
+                                   conductance="throat.diffusive_conductance"))
+        self.settings._update(kwargs)
+
+
+class OhmicConduction(ReactiveTransport):
+    """_ohmic_conduction.py:22-23"""
+
+    def __init__(self, network, phase, name="ohmic_?", **kwargs):
+        super().__init__(network=network, phase=phase, name=name, **kwargs)
+        self.settings._update(dict(quantity="pore.voltage",
+                                   conductance="throat.electrical_conductance"))
+        self.settings._update(kwargs)
+
+
+class FourierConduction(ReactiveTransport):
+    """_fourier_conduction.py:22-23"""
+
+    def __init__(self, network, phase, name="fourier_?", **kwargs):
+        super().__init__(network=network, phase=phase, name=name, **kwargs)
+        self.settings._update(dict(quantity="pore.temperature",
+                                   conductance="throat.thermal_conductance"))
+        self.settings._update(kwargs)

@@ -1,0 +1,235 @@
+// common.cuh -- context, buffers, scan and reduction primitives shared by the
+// kernels of libb200pnm.so (sm_100a).  No reference counterpart: the reference
+// (pure Python) delegates all of this to numpy/scipy.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "b200pnm.h"
+
+#define B200_MAX_SRC 8
+#define B200_MAX_DIAGS 8
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct SrcTerm {
+  int kind;
+  const uint8_t* mask;
+  const double *p1, *p2, *p3;
+};
+struct SrcPack {
+  int n;
+  SrcTerm s[B200_MAX_SRC];
+};
+
+struct DiaPack {
+  int nd;
+  int off[B200_MAX_DIAGS];
+  const double* v[B200_MAX_DIAGS];  // each points at row 0 of the owned range
+};
+
+// device-side scalar slots of the PCG (all doubles, in ctx->scal)
+// pair p (iteration parity): [2p] = r.r, [2p+1] = sum d_i r_i^2 (the unscaled
+// residual norm^2); the pair is contiguous so one all-reduce covers both.
+enum {
+  SC_RR0 = 0,
+  SC_TRUE0 = 1,
+  SC_RR1 = 2,
+  SC_TRUE1 = 3,
+  SC_PAP = 4,   // p.Ap
+  SC_BNORM = 5, // ||b||^2
+  SC_AUX0 = 6,
+  SC_AUX1 = 7,
+  SC_AUX2 = 8,
+  SC_COUNT = 16
+};
+
+struct b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+  int64_t launches = 0;
+
+  // ownership (slab); single GPU: row_begin = 0, row_end = n_global
+  int64_t n_global = 0, row_begin = 0, row_end = 0, n = 0;
+  int nranks = 1, rank = 0;
+  void* nccl = nullptr;  // ncclComm_t
+
+  // pure Laplacian, canonical CSR of the owned rows (global column ids)
+  DevBuf pure_indptr, pure_indices, pure_data, pure_diag;
+  int64_t pure_nnz = 0;
+  bool have_pure = false;
+
+  // system matrix (after BCs, or loaded), b, diagonal bookkeeping
+  DevBuf sys_indptr, sys_indices, sys_data, sys_diag, sys_diagpos, b;
+  int64_t sys_nnz = 0;
+  bool have_sys = false;
+  bool sys_generic = false;   // came from load_coo/load_csr: symmetry unknown
+  double f = 0.0;
+  bool f_override = false;
+  uint64_t sys_epoch = 0;     // bumped whenever structure/values change
+
+  // sources
+  SrcPack srcs{};
+  DevBuf diag_eff, b_eff;     // linearised diagonal and rhs
+  bool lin_valid = false;
+
+  // PCG operator (Jacobi-scaled, unit diagonal)
+  uint64_t op_epoch = ~0ull;
+  int fmt = B200_FMT_NONE;
+  int force_fmt = 0;
+  bool unit_diag = true;
+  int64_t pad = 0;            // halo/padding entries on each side of vectors
+  DevBuf sc;                  // s_i = d_i^-1/2, padded layout
+  DevBuf dexp;                // explicit diagonal when !unit_diag
+  DiaPack dia{};
+  DevBuf dia_store;
+  DevBuf o_indptr, o_cols, o_vals, o_rowstart;  // scaled off-diagonal CSR
+  int64_t o_nnz = 0, o_nblocks = 0, o_maxrow = 0;
+  DevBuf vx, vr, vp, vap, vb;  // PCG vectors (padded layout)
+  DevBuf scal;                 // SC_COUNT doubles
+  double* scal_h = nullptr;    // pinned mirror
+
+  // workspaces
+  DevBuf w_cnt, w_keys, w_scan, w_part, w_ticket, w_flags, w_tmp0, w_tmp1, w_tmp2;
+  int* flags_h = nullptr;      // pinned
+
+  // statistics
+  b200_stats stats{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+};
+
+// ---------------------------------------------------------------- error glue
+#define CK(call)                                                              \
+  do {                                                                        \
+    cudaError_t _e = (call);                                                  \
+    if (_e != cudaSuccess) {                                                  \
+      char _buf[512];                                                         \
+      snprintf(_buf, sizeof _buf, "%s:%d: %s -> %s", __FILE__, __LINE__, #call,\
+               cudaGetErrorString(_e));                                       \
+      ctx->err = _buf;                                                        \
+      return B200_ERR_CUDA;                                                   \
+    }                                                                         \
+  } while (0)
+
+#define FAIL(code, ...)                                                       \
+  do {                                                                        \
+    char _buf[512];                                                           \
+    snprintf(_buf, sizeof _buf, __VA_ARGS__);                                 \
+    ctx->err = _buf;                                                          \
+    return (code);                                                            \
+  } while (0)
+
+#define RET(call)                                                             \
+  do {                                                                        \
+    int _r = (call);                                                          \
+    if (_r != B200_OK) return _r;                                             \
+  } while (0)
+
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                             \
+  do {                                                                        \
+    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);            \
+    (ctx)->launches++;                                                        \
+  } while (0)
+
+static inline int grid_for(int64_t n, int block, int per_thread = 1) {
+  int64_t g = (n + (int64_t)block * per_thread - 1) / ((int64_t)block * per_thread);
+  if (g < 1) g = 1;
+  const int64_t cap = 148 * 16;   // 148 SMs x 16 resident CTAs: grid-stride beyond
+  return (int)(g > cap ? cap : g);
+}
+
+// --------------------------------------------------------- device reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum; result valid in thread 0.  Fixed order -> deterministic.
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();           // protect sh against a previous call
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+  if (w == 0) v = warp_sum(v);
+  return v;
+}
+
+// Grid-wide deterministic sum of NV values per block: every block stores its
+// partials, the last block to arrive (integer ticket) adds them in a fixed
+// order and writes out[k].  No floating-point atomics anywhere.
+template <int NV>
+__device__ __forceinline__ void grid_sum_finalize(const double (&v)[NV], double* part,
+                                                  unsigned* ticket, double* const (&out)[NV]) {
+  __shared__ bool is_last;
+  double bs[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) bs[k] = block_sum(v[k]);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) part[(size_t)k * gridDim.x + blockIdx.x] = bs[k];
+    __threadfence();
+    unsigned t = atomicInc(ticket, gridDim.x - 1);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = 0.0;
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x)
+        s += __ldcg(&part[(size_t)k * gridDim.x + i]);
+      s = block_sum(s);
+      if (threadIdx.x == 0) *out[k] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------ host helpers
+int b200_scan_exclusive_i32(b200_ctx* ctx, const int* in, int* out, int64_t n,
+                            int64_t* total_h);
+int b200_check_flags(b200_ctx* ctx);   // reads w_flags, maps to an error code
+int b200_zero_flags(b200_ctx* ctx);
+
+enum { FLAG_INDEX = 0, FLAG_NONFINITE = 1, FLAG_NONPOS_DIAG = 2, FLAG_OVERFLOW = 3,
+       FLAG_NONSYM = 4, FLAG_ZERO_DIAG = 5, FLAG_COUNT = 8 };
+
+// dist.cu (no-ops when nranks == 1)
+int b200_halo_exchange(b200_ctx* ctx, double* base);           // padded vector
+int b200_allreduce_sum(b200_ctx* ctx, double* dev, int count); // in place, fp64
+int b200_allreduce_max_host(b200_ctx* ctx, int64_t* v);
+// solver.cu
+int b200_linearize(b200_ctx* ctx, const double* x);
+int b200_residual_norms(b200_ctx* ctx, const double* x, double* res2, double* x2);
+int b200_spmv_csr_raw(b200_ctx* ctx, const int* indptr, const int* indices,
+                      const double* data, int64_t n, int64_t col_shift,
+                      const double* x, double* y);

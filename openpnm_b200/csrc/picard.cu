@@ -1,0 +1,200 @@
+// picard.cu -- K5 (device Picard / Newton-linearised outer loop) and K6 (rate).
+//
+// Reference behaviour replaced (file:line under /root/reference):
+//   openpnm/algorithms/_reactive_transport.py:150-213  _run_special outer loop
+//   openpnm/algorithms/_reactive_transport.py:234-244  _get_residual = A x - b
+//   openpnm/algorithms/_transport.py:209-221           solve + relaxation
+//   openpnm/algorithms/_solution.py:17-20              first-dx aliasing quirk
+//   scipy/optimize/_nonlin.py TerminationCondition.check (f_tol = x_tol = inf)
+//   openpnm/algorithms/_transport.py:259-330           rate()
+#include "common.cuh"
+
+extern "C" int b200_clear_sources(b200_ctx* ctx) {
+  if (!ctx) return B200_ERR_ARG;
+  ctx->srcs.n = 0;
+  ctx->lin_valid = false;
+  ctx->op_epoch = ~0ull;
+  return B200_OK;
+}
+
+extern "C" int b200_add_source(b200_ctx* ctx, int kind, const uint8_t* mask, const double* p1,
+                               const double* p2, const double* p3) {
+  if (!ctx) return B200_ERR_ARG;
+  if (ctx->srcs.n >= B200_MAX_SRC) FAIL(B200_ERR_ARG, "at most %d source terms", B200_MAX_SRC);
+  if (kind < B200_SRC_LINEAR || kind > B200_SRC_STANDARD_KINETICS || !mask || !p1 || !p2)
+    FAIL(B200_ERR_ARG, "add_source: bad arguments");
+  SrcTerm& s = ctx->srcs.s[ctx->srcs.n++];
+  s.kind = kind; s.mask = mask; s.p1 = p1; s.p2 = p2; s.p3 = p3;
+  ctx->lin_valid = false;
+  ctx->op_epoch = ~0ull;
+  return B200_OK;
+}
+
+// x <- w x_new + (1-w) x ; returns ||x - xold||^2 (xold = x before the update)
+__global__ void __launch_bounds__(256) k_relax(double* __restrict__ x,
+                                               const double* __restrict__ xnew, double w,
+                                               int64_t n, double* part, unsigned* ticket,
+                                               double* out_dx2, int* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double s = 0.0;
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double xo = x[i];
+    const double xn = w * xnew[i] + (1.0 - w) * xo;
+    x[i] = xn;
+    const double dx = xn - xo;
+    s += dx * dx;
+    if (!isfinite(xn)) bad = true;
+  }
+  if (bad) flags[FLAG_NONFINITE] = 1;
+  double v[1] = {s};
+  double* o[1] = {out_dx2};
+  grid_sum_finalize<1>(v, part, ticket, o);
+}
+
+__global__ void k_check_finite(const double* __restrict__ a, int64_t n, int* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    if (!isfinite(a[i])) bad = true;
+  if (bad) flags[FLAG_NONFINITE] = 1;
+}
+
+extern "C" int b200_picard(b200_ctx* ctx, const double* x0, double relaxation,
+                           int64_t newton_maxiter, double f_rtol, double x_rtol, double cg_rtol,
+                           int64_t cg_maxiter, double* x, int64_t* num_iter, int* converged,
+                           int64_t* cg_iters_total, int* last_info) {
+  if (!ctx || !ctx->have_sys || !x) {
+    if (ctx) ctx->err = "picard: apply_bcs / load a system first";
+    return B200_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  const int64_t n = ctx->n;
+  CK(ctx->w_part.ensure((size_t)4 * 148 * 16 * sizeof(double)));
+  if (!ctx->w_ticket.p) {
+    CK(ctx->w_ticket.ensure(64));
+    CK(cudaMemsetAsync(ctx->w_ticket.p, 0, 64, ctx->stream));
+  }
+  CK(ctx->scal.ensure(SC_COUNT * sizeof(double)));
+  CK(ctx->w_tmp0.ensure((size_t)n * sizeof(double)));   // x_new
+  RET(b200_zero_flags(ctx));
+  int* flags = ctx->w_flags.as<int>();
+  double* xnew = ctx->w_tmp0.as<double>();
+  if (x0) {
+    if (x0 != x)
+      CK(cudaMemcpyAsync(x, x0, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    // _validate_x0 (_transport.py:229-233)
+    LAUNCH(ctx, k_check_finite, grid_for(n, 256), 256, 0, x, n, flags);
+    CK(cudaMemcpyAsync(ctx->flags_h, flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->flags_h[FLAG_NONFINITE]) FAIL(B200_ERR_NONFINITE, "x0 contains inf/nan values");
+  } else {
+    CK(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), ctx->stream));
+  }
+  RET(b200_linearize(ctx, x));
+
+  double f0 = -1.0, dx2 = 0.0;
+  int64_t iters = 0, cg_total = 0;
+  int conv = 0, info = 0;
+  bool first = true;
+  for (int64_t i = 0; i < newton_maxiter; ++i) {
+    double r2 = 0.0, x2 = 0.0;
+    RET(b200_residual_norms(ctx, x, &r2, &x2));
+    const double fn = sqrt(r2), xn = sqrt(x2), dxn = sqrt(dx2);
+    if (f0 < 0.0) f0 = fn;
+    // TerminationCondition.check: f_tol = inf, x_tol = inf
+    if (fn == 0.0 || (fn / f_rtol <= f0 && dxn / x_rtol <= xn)) { conv = 1; break; }
+    // _validate_linear_system (_transport.py:253-257)
+    CK(cudaMemcpyAsync(ctx->flags_h, flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->flags_h[FLAG_NONFINITE] || !isfinite(fn))
+      FAIL(B200_ERR_NONFINITE, "A or b contains inf/nan values");
+    int64_t its = 0;
+    double rel = 0.0;
+    RET(b200_pcg(ctx, x, cg_rtol, 0.0, cg_maxiter, xnew, &its, &rel, &info));
+    cg_total += its;
+    double* sc = ctx->scal.as<double>();
+    LAUNCH(ctx, k_relax, grid_for(n, 256, 2), 256, 0, x, xnew, relaxation, n,
+           ctx->w_part.as<double>(), ctx->w_ticket.as<unsigned>(), sc + SC_AUX0, flags);
+    CK(cudaMemcpyAsync(ctx->scal_h + SC_AUX0, sc + SC_AUX0, sizeof(double), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    dx2 = first ? 0.0 : ctx->scal_h[SC_AUX0];   // aliasing quirk: first dx == 0
+    first = false;
+    RET(b200_linearize(ctx, x));
+    iters = i + 1;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (num_iter) *num_iter = iters;
+  if (converged) *converged = conv;
+  if (cg_iters_total) *cg_iters_total = cg_total;
+  if (last_info) *last_info = info;
+  return B200_OK;
+}
+
+// ==================================================================== K6: rate
+// Net rate leaving pore i = sum_t g_t (x_i - x_nbr) = (L_pure x)_i: one row of
+// the pure CSR per requested pore, 8 lanes per row.
+__global__ void __launch_bounds__(256) k_rate_pores(const int* __restrict__ indptr,
+                                                    const int* __restrict__ indices,
+                                                    const double* __restrict__ data,
+                                                    const double* __restrict__ x,
+                                                    const long long* __restrict__ pores, int64_t k,
+                                                    int64_t rb, int64_t n, double* __restrict__ out,
+                                                    int* __restrict__ flags) {
+  constexpr int G = 8;
+  const int lane = threadIdx.x % G;
+  const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) / G;
+  for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; q < k; q += gstride) {
+    const int64_t r = pores[q] - rb;
+    double s = 0.0;
+    if (r < 0 || r >= n) {
+      if (lane == 0) flags[FLAG_INDEX] = 1;
+    } else {
+      for (int e = indptr[r] + lane; e < indptr[r + 1]; e += G) s += data[e] * x[indices[e]];
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
+    if (lane == 0) out[q] = s;
+  }
+}
+
+extern "C" int b200_rate_pores(b200_ctx* ctx, const double* x, const int64_t* pores, int64_t k,
+                               double* out) {
+  if (!ctx || !ctx->have_pure) {
+    if (ctx) ctx->err = "rate: build_laplacian first";
+    return B200_ERR_ARG;
+  }
+  if (k <= 0) return B200_OK;
+  RET(b200_zero_flags(ctx));
+  LAUNCH(ctx, k_rate_pores, grid_for(k * 8, 256), 256, 0, ctx->pure_indptr.as<int>(),
+         ctx->pure_indices.as<int>(), ctx->pure_data.as<double>(), x,
+         reinterpret_cast<const long long*>(pores), k, ctx->row_begin, ctx->n, out,
+         ctx->w_flags.as<int>());
+  CK(cudaGetLastError());
+  return b200_check_flags(ctx);
+}
+
+__global__ void k_rate_throats(const longlong2* __restrict__ conns, const double* __restrict__ g,
+                               const double* __restrict__ x, const long long* __restrict__ throats,
+                               int64_t k, double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < k; q += stride) {
+    const long long t = throats[q];
+    const longlong2 c = conns[t];
+    out[q] = fabs(g[t] * (x[c.y] - x[c.x]));
+  }
+}
+
+extern "C" int b200_rate_throats(b200_ctx* ctx, const int64_t* conns, const double* g,
+                                 const double* x, const int64_t* throats, int64_t k, double* out) {
+  if (!ctx) return B200_ERR_ARG;
+  if (k <= 0) return B200_OK;
+  LAUNCH(ctx, k_rate_throats, grid_for(k, 256), 256, 0, reinterpret_cast<const longlong2*>(conns),
+         g, x, reinterpret_cast<const long long*>(throats), k, out);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}

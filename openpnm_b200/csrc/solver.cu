@@ -1,0 +1,919 @@
+// solver.cu -- K3 (SpMV), K4 (Jacobi-PCG on the symmetrically scaled operator),
+// source linearisation (part of K5).  sm_100a, fp64, HBM-bound kernels.
+//
+// Reference behaviour replaced (file:line under /root/reference):
+//   openpnm/solvers/_scipy.py:18-26   ScipyCG.solve: cg(A, b, tol, atol=|b|*tol)
+//   openpnm/solvers/_base.py:21-63    IterativeSolver(tol, maxiter), residual
+//   openpnm/algorithms/_reactive_transport.py:125-148  _apply_sources
+//   openpnm/models/physics/source_terms/_funcs.py:21-168 linearised sources
+//
+// Operator formats (the PCG never touches the canonical CSR again):
+//   DIA  : the matrix has <= 8 distinct super-diagonals (any lattice network in
+//          index order).  Symmetric half storage: one fp64 array per
+//          super-diagonal, no indices, unit main diagonal implied.
+//          y_i = x_i + sum_m v_m[i] x[i+k_m] + v_m[i-k_m] x[i-k_m]
+//   CSR  : everything else (Delaunay/Voronoi): off-diagonals only, int32
+//          local column + fp64 value, streamed coalesced through shared memory
+//          in fixed-size row blocks ("CSR-stream"), unit diagonal implied.
+// Vectors live in a padded layout [pad | n owned | pad] so that neighbour
+// reads i +/- k never need a bounds check; in slab mode the pads are the
+// halo windows filled by the neighbour ranks.
+#include "common.cuh"
+
+#define PCG_T 256
+
+static inline double* owned(const DevBuf& b, int64_t pad) { return b.as<double>() + pad; }
+
+static inline const double* cur_diag(b200_ctx* ctx) {
+  return (ctx->srcs.n > 0 && ctx->lin_valid) ? ctx->diag_eff.as<double>() : ctx->sys_diag.as<double>();
+}
+static inline const double* cur_b(b200_ctx* ctx) {
+  return (ctx->srcs.n > 0 && ctx->lin_valid) ? ctx->b_eff.as<double>() : ctx->b.as<double>();
+}
+
+static int ensure_ws(b200_ctx* ctx) {
+  CK(ctx->w_part.ensure((size_t)4 * 148 * 16 * sizeof(double)));
+  if (!ctx->w_ticket.p) {
+    CK(ctx->w_ticket.ensure(64));
+    CK(cudaMemsetAsync(ctx->w_ticket.p, 0, 64, ctx->stream));
+  }
+  CK(ctx->scal.ensure(SC_COUNT * sizeof(double)));
+  CK(ctx->w_flags.ensure(FLAG_COUNT * sizeof(int)));
+  return B200_OK;
+}
+
+// ======================================================== raw CSR SpMV (K3)
+// y = M x on a canonical CSR (diagonal stored).  8 lanes per row; used for
+// b200_spmv, residuals and rate(), not inside the PCG loop.
+template <int G>
+__global__ void __launch_bounds__(256) k_spmv_csr_vec(const int* __restrict__ indptr,
+                                                      const int* __restrict__ indices,
+                                                      const double* __restrict__ data, int64_t n,
+                                                      int64_t col_shift,
+                                                      const double* __restrict__ x,
+                                                      double* __restrict__ y) {
+  const int lane = threadIdx.x % G;
+  const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) / G;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; r < n; r += gstride) {
+    double s = 0.0;
+    const int e1 = indptr[r + 1];
+    for (int e = indptr[r] + lane; e < e1; e += G) s += data[e] * x[indices[e] - col_shift];
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
+    if (lane == 0) y[r] = s;
+  }
+}
+
+int b200_spmv_csr_raw(b200_ctx* ctx, const int* indptr, const int* indices, const double* data,
+                      int64_t n, int64_t col_shift, const double* x, double* y) {
+  LAUNCH(ctx, k_spmv_csr_vec<8>, grid_for(n * 8, 256), 256, 0, indptr, indices, data, n,
+         col_shift, x, y);
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_spmv(b200_ctx* ctx, int which, const double* x, double* y) {
+  if (!ctx) return B200_ERR_ARG;
+  if (which == B200_MAT_PURE) {
+    if (!ctx->have_pure) FAIL(B200_ERR_ARG, "no pure matrix");
+    return b200_spmv_csr_raw(ctx, ctx->pure_indptr.as<int>(), ctx->pure_indices.as<int>(),
+                             ctx->pure_data.as<double>(), ctx->n, 0, x, y);
+  }
+  if (!ctx->have_sys) FAIL(B200_ERR_ARG, "no system matrix");
+  return b200_spmv_csr_raw(ctx, ctx->sys_indptr.as<int>(), ctx->sys_indices.as<int>(),
+                           ctx->sys_data.as<double>(), ctx->n, 0, x, y);
+}
+
+// =============================================== source linearisation (K5a)
+// diag_eff = diag - sum_s S1_s, b_eff = b + sum_s S2_s on the masked pores,
+// S1/S2 evaluated at X = x (source_terms/_funcs.py:61-69,108-116,158-168), and
+// the diagonal entry of the system CSR is patched so residuals see it.
+__device__ __forceinline__ void src_eval(int kind, double X, double p1, double p2, double p3,
+                                         double& S1, double& S2) {
+  if (kind == B200_SRC_LINEAR) {            // r = A1 X + A2
+    S1 = p1;
+    S2 = p2;
+  } else if (kind == B200_SRC_POWER_LAW) {  // r = A X^B + C
+    const double xb = pow(X, p2);
+    S1 = p1 * p2 * pow(X, p2 - 1.0);
+    S2 = p1 * xb * (1.0 - p2) + p3;
+  } else {                                  // standard kinetics r = A X^b
+    const double xb = pow(X, p2);
+    S1 = p1 * p2 * pow(X, p2 - 1.0);
+    S2 = p1 * (1.0 - p2) * xb;
+  }
+}
+
+__global__ void k_linearize(SrcPack sp, const double* __restrict__ x,
+                            const double* __restrict__ diag0, const double* __restrict__ b0,
+                            const int* __restrict__ diagpos, int64_t n,
+                            double* __restrict__ diag_eff, double* __restrict__ b_eff,
+                            double* __restrict__ sys_data, int* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double d = diag0[i], bb = b0[i];
+    const double X = x[i];
+    for (int s = 0; s < sp.n; ++s) {
+      if (sp.s[s].mask[i]) {
+        double S1, S2;
+        src_eval(sp.s[s].kind, X, sp.s[s].p1[i], sp.s[s].p2[i], sp.s[s].p3 ? sp.s[s].p3[i] : 0.0,
+                 S1, S2);
+        d += -S1;
+        bb += S2;
+      }
+    }
+    if (!isfinite(d) || !isfinite(bb)) bad = true;
+    diag_eff[i] = d;
+    b_eff[i] = bb;
+    const int dp = diagpos[i];
+    if (dp >= 0) sys_data[dp] = d;
+  }
+  if (bad) flags[FLAG_NONFINITE] = 1;
+}
+
+int b200_linearize(b200_ctx* ctx, const double* x) {
+  if (!ctx->have_sys) FAIL(B200_ERR_ARG, "no system matrix");
+  if (ctx->srcs.n == 0) {
+    ctx->lin_valid = true;
+    return B200_OK;
+  }
+  const int64_t n = ctx->n;
+  RET(ensure_ws(ctx));
+  CK(ctx->diag_eff.ensure((size_t)n * sizeof(double)));
+  CK(ctx->b_eff.ensure((size_t)n * sizeof(double)));
+  LAUNCH(ctx, k_linearize, grid_for(n, 256), 256, 0, ctx->srcs, x, ctx->sys_diag.as<double>(),
+         ctx->b.as<double>(), ctx->sys_diagpos.as<int>(), n, ctx->diag_eff.as<double>(),
+         ctx->b_eff.as<double>(), ctx->sys_data.as<double>(), ctx->w_flags.as<int>());
+  CK(cudaGetLastError());
+  ctx->lin_valid = true;
+  ctx->op_epoch = ~0ull;   // scaling depends on the diagonal
+  return B200_OK;
+}
+
+// residual R = A x - b with the current linearisation; returns ||R||^2, ||x||^2
+__global__ void __launch_bounds__(256) k_residual_norms(const int* __restrict__ indptr,
+                                                        const int* __restrict__ indices,
+                                                        const double* __restrict__ data,
+                                                        const double* __restrict__ b,
+                                                        const double* __restrict__ x, int64_t n,
+                                                        double* part, unsigned* ticket,
+                                                        double* out_r2, double* out_x2) {
+  constexpr int G = 8;
+  const int lane = threadIdx.x % G;
+  const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) / G;
+  double r2 = 0.0, x2 = 0.0;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; r < n; r += gstride) {
+    double s = 0.0;
+    const int e1 = indptr[r + 1];
+    for (int e = indptr[r] + lane; e < e1; e += G) s += data[e] * x[indices[e]];
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
+    if (lane == 0) {
+      const double res = s - b[r];
+      r2 += res * res;
+      x2 += x[r] * x[r];
+    }
+  }
+  double v[2] = {r2, x2};
+  double* o[2] = {out_r2, out_x2};
+  grid_sum_finalize<2>(v, part, ticket, o);
+}
+
+int b200_residual_norms(b200_ctx* ctx, const double* x, double* res2, double* x2) {
+  RET(ensure_ws(ctx));
+  double* sc = ctx->scal.as<double>();
+  LAUNCH(ctx, k_residual_norms, grid_for(ctx->n * 8, 256), 256, 0, ctx->sys_indptr.as<int>(),
+         ctx->sys_indices.as<int>(), ctx->sys_data.as<double>(), cur_b(ctx), x, ctx->n,
+         ctx->w_part.as<double>(), ctx->w_ticket.as<unsigned>(), sc + SC_AUX0, sc + SC_AUX1);
+  CK(cudaMemcpyAsync(ctx->scal_h + SC_AUX0, sc + SC_AUX0, 2 * sizeof(double),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *res2 = ctx->scal_h[SC_AUX0];
+  *x2 = ctx->scal_h[SC_AUX1];
+  return B200_OK;
+}
+
+// ============================================================ operator setup
+struct OffTable {
+  int n;                      // number of distinct positive offsets found
+  int off[B200_MAX_DIAGS];
+  int overflow;
+  int maxband;
+};
+
+// distinct positive offsets (col - row) of the system matrix; integer CAS only
+__global__ void k_detect_offsets(const int* __restrict__ indptr, const int* __restrict__ indices,
+                                 int64_t n, int64_t rb, OffTable* tab) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int mymax = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    const int64_t gi = r + rb;
+    for (int e = indptr[r]; e < indptr[r + 1]; ++e) {
+      const int64_t o64 = (int64_t)indices[e] - gi;
+      const int ao = (int)(o64 < 0 ? -o64 : o64);
+      if (ao > mymax) mymax = ao;
+      if (o64 <= 0) continue;
+      const int o = (int)o64;
+      bool found = false;
+      for (int k = 0; k < B200_MAX_DIAGS && !found; ++k) {
+        int cur = tab->off[k];      // may be stale (L1): the CAS below is the truth
+        if (cur == 0) cur = atomicCAS(&tab->off[k], 0, o);
+        if (cur == 0 || cur == o) found = true;
+      }
+      if (!found) tab->overflow = 1;
+    }
+  }
+  if (mymax > 0) atomicMax(&tab->maxband, mymax);
+}
+
+// s_i = d_i^-1/2 in the padded layout; singleton[i] = row has no off-diagonal
+__global__ void k_scale(const double* __restrict__ diag, int64_t n, int unit,
+                        double* __restrict__ s_owned, int* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool nonpos = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double d = diag[i];
+    if (!(d > 0.0) || !isfinite(d)) nonpos = true;
+    s_owned[i] = unit ? ((d > 0.0) ? 1.0 / sqrt(d) : 1.0) : 1.0;
+  }
+  if (nonpos) flags[FLAG_NONPOS_DIAG] = 1;
+}
+
+__device__ __forceinline__ int off_lookup(const OffTable& t, int o) {
+#pragma unroll
+  for (int k = 0; k < B200_MAX_DIAGS; ++k)
+    if (k < t.n && t.off[k] == o) return k;
+  return -1;
+}
+
+// scatter the scaled upper triangle into the diagonal arrays; lower entries
+// that point below the owned range land in the front pad of their diagonal.
+__global__ void k_build_dia(const int* __restrict__ indptr, const int* __restrict__ indices,
+                            const double* __restrict__ data, int64_t n, int64_t rb,
+                            const double* __restrict__ s_owned, OffTable tab, double* vstore,
+                            int64_t vstride, int64_t pad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    const int64_t gi = r + rb;
+    const double sr = s_owned[r];
+    for (int e = indptr[r]; e < indptr[r + 1]; ++e) {
+      const int64_t j = indices[e];
+      const int64_t o = j - gi;
+      if (o == 0) continue;
+      const int64_t lj = j - rb;
+      if (o > 0) {
+        const int m = off_lookup(tab, (int)o);
+        vstore[(int64_t)m * vstride + pad + r] = data[e] * sr * s_owned[lj];
+      } else if (lj < 0) {
+        const int m = off_lookup(tab, (int)(-o));
+        vstore[(int64_t)m * vstride + pad + lj] = data[e] * sr * s_owned[lj];
+      }
+    }
+  }
+}
+
+// generic matrices only: every lower entry must mirror the stored upper one
+__global__ void k_check_sym_dia(const int* __restrict__ indptr, const int* __restrict__ indices,
+                                const double* __restrict__ data, int64_t n, int64_t rb,
+                                const double* __restrict__ s_owned, OffTable tab,
+                                const double* vstore, int64_t vstride, int64_t pad,
+                                int* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    const int64_t gi = r + rb;
+    const double sr = s_owned[r];
+    for (int e = indptr[r]; e < indptr[r + 1]; ++e) {
+      const int64_t j = indices[e];
+      const int64_t o = j - gi;
+      const int64_t lj = j - rb;
+      if (o >= 0 || lj < 0) continue;
+      const int m = off_lookup(tab, (int)(-o));
+      if (m < 0) { bad = true; continue; }
+      const double a = data[e] * sr * s_owned[lj];
+      const double u = vstore[(int64_t)m * vstride + pad + lj];
+      if (fabs(a - u) > 1e-12 * fmax(fabs(a), fabs(u))) bad = true;
+    }
+  }
+  if (bad) flags[FLAG_NONSYM] = 1;
+}
+
+// scaled off-diagonal CSR: counts, then values + local signed columns
+__global__ void k_offdiag_count(const int* __restrict__ indptr, const int* __restrict__ diagpos,
+                                int64_t n, int* __restrict__ cnt, int* __restrict__ maxrow) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int mx = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    int c = indptr[r + 1] - indptr[r] - (diagpos[r] >= 0 ? 1 : 0);
+    cnt[r] = c;
+    if (c > mx) mx = c;
+  }
+  atomicMax(maxrow, mx);
+}
+
+__global__ void k_offdiag_emit(const int* __restrict__ indptr, const int* __restrict__ indices,
+                               const double* __restrict__ data, int64_t n, int64_t rb,
+                               const double* __restrict__ s_owned, const int* __restrict__ optr,
+                               int* __restrict__ ocols, double* __restrict__ ovals) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    const int64_t gi = r + rb;
+    const double sr = s_owned[r];
+    int o = optr[r];
+    for (int e = indptr[r]; e < indptr[r + 1]; ++e) {
+      const int64_t j = indices[e];
+      if (j == gi) continue;
+      const int64_t lj = j - rb;
+      ocols[o] = (int)lj;
+      ovals[o] = data[e] * sr * s_owned[lj];
+      ++o;
+    }
+  }
+}
+
+// row blocks for the CSR-stream kernel: block q owns the rows whose work
+// counter (entries before the row + row index) falls in [q*Q, (q+1)*Q)
+__global__ void k_rowstart(const int* __restrict__ optr, int64_t n, int64_t Q, int64_t nblocks,
+                           int* __restrict__ rowstart) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q > nblocks) return;
+  if (q == nblocks) { rowstart[q] = (int)n; return; }
+  const int64_t target = q * Q;
+  int64_t lo = 0, hi = n;   // first r with optr[r] + r >= target
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)optr[mid] + mid >= target) hi = mid; else lo = mid + 1;
+  }
+  rowstart[q] = (int)lo;
+}
+
+#define CSR_Q 2048          // work units (entries + rows) per CTA
+#define CSR_MAXROW 4096     // longest row the streaming kernel accepts
+
+static int prepare_operator(b200_ctx* ctx) {
+  const int64_t n = ctx->n;
+  RET(ensure_ws(ctx));
+  if (!ctx->lin_valid) RET(b200_linearize(ctx, nullptr));   // no sources: trivial
+  CK(cudaMemsetAsync(ctx->w_flags.p, 0, FLAG_COUNT * sizeof(int), ctx->stream));
+  int* flags = ctx->w_flags.as<int>();
+  const int* indptr = ctx->sys_indptr.as<int>();
+  const int* indices = ctx->sys_indices.as<int>();
+  const double* data = ctx->sys_data.as<double>();
+
+  // ---- structure: offsets + bandwidth
+  CK(ctx->w_tmp2.ensure(sizeof(OffTable)));
+  OffTable* dtab = ctx->w_tmp2.as<OffTable>();
+  CK(cudaMemsetAsync(dtab, 0, sizeof(OffTable), ctx->stream));
+  LAUNCH(ctx, k_detect_offsets, grid_for(n, 128), 128, 0, indptr, indices, n, ctx->row_begin, dtab);
+  OffTable tab;
+  CK(cudaMemcpyAsync(&tab, dtab, sizeof tab, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  tab.n = 0;
+  for (int k = 0; k < B200_MAX_DIAGS; ++k)
+    if (tab.off[k] != 0) tab.n = k + 1;
+  const int64_t upper = (ctx->sys_nnz - n) / 2;   // off-diagonals are symmetric pairs
+  bool want_dia = !tab.overflow && tab.n > 0 &&
+                  (double)upper >= 0.25 * (double)tab.n * (double)n;
+  if (ctx->force_fmt == B200_FMT_CSR) want_dia = false;
+  if (ctx->force_fmt == B200_FMT_DIA && (tab.overflow || tab.n == 0))
+    FAIL(B200_ERR_ARG, "DIA format forced but the matrix has more than %d diagonals",
+         B200_MAX_DIAGS);
+  if (ctx->force_fmt == B200_FMT_DIA) want_dia = true;
+  int64_t pad = (want_dia || ctx->nranks > 1) ? tab.maxband : 0;
+  RET(b200_allreduce_max_host(ctx, &pad));          // every rank uses the same halo width
+  pad = (pad + 31) / 32 * 32;
+  if (ctx->nranks > 1 && pad > n)
+    FAIL(B200_ERR_ARG, "slab of %lld rows is thinner than the matrix half-bandwidth %lld",
+         (long long)n, (long long)pad);
+  ctx->pad = pad;
+  const size_t vbytes = (size_t)(n + 2 * pad) * sizeof(double);
+
+  // ---- scaling
+  CK(ctx->sc.ensure(vbytes));
+  CK(cudaMemsetAsync(ctx->sc.p, 0, vbytes, ctx->stream));
+  double* s_owned = owned(ctx->sc, pad);
+  LAUNCH(ctx, k_scale, grid_for(n, 256), 256, 0, cur_diag(ctx), n, 1, s_owned, flags);
+  CK(cudaMemcpyAsync(ctx->flags_h, flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->unit_diag = !ctx->flags_h[FLAG_NONPOS_DIAG];
+  if (!ctx->unit_diag) {
+    // indefinite / semi-definite diagonal: no scaling, explicit diagonal, CSR
+    LAUNCH(ctx, k_scale, grid_for(n, 256), 256, 0, cur_diag(ctx), n, 0, s_owned, flags);
+    CK(ctx->dexp.ensure((size_t)n * sizeof(double)));
+    CK(cudaMemcpyAsync(ctx->dexp.p, cur_diag(ctx), (size_t)n * sizeof(double),
+                       cudaMemcpyDeviceToDevice, ctx->stream));
+    want_dia = false;
+  }
+  RET(b200_halo_exchange(ctx, ctx->sc.as<double>()));   // s of the halo columns
+
+  for (DevBuf* v : {&ctx->vx, &ctx->vr, &ctx->vp, &ctx->vap, &ctx->vb}) {
+    CK(v->ensure(vbytes));
+    CK(cudaMemsetAsync(v->p, 0, vbytes, ctx->stream));
+  }
+
+  if (want_dia) {
+    const int64_t vstride = n + pad;
+    CK(ctx->dia_store.ensure((size_t)tab.n * vstride * sizeof(double)));
+    CK(cudaMemsetAsync(ctx->dia_store.p, 0, (size_t)tab.n * vstride * sizeof(double), ctx->stream));
+    LAUNCH(ctx, k_build_dia, grid_for(n, 128), 128, 0, indptr, indices, data, n, ctx->row_begin,
+           s_owned, tab, ctx->dia_store.as<double>(), vstride, pad);
+    if (ctx->sys_generic) {
+      LAUNCH(ctx, k_check_sym_dia, grid_for(n, 128), 128, 0, indptr, indices, data, n,
+             ctx->row_begin, s_owned, tab, ctx->dia_store.as<double>(), vstride, pad, flags);
+      CK(cudaMemcpyAsync(ctx->flags_h, flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost,
+                         ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      if (ctx->flags_h[FLAG_NONSYM]) want_dia = false;
+    }
+    if (want_dia) {
+      ctx->dia.nd = tab.n;
+      for (int k = 0; k < tab.n; ++k) {
+        ctx->dia.off[k] = tab.off[k];
+        ctx->dia.v[k] = ctx->dia_store.as<double>() + (int64_t)k * vstride + pad;
+      }
+      ctx->fmt = B200_FMT_DIA;
+    }
+  }
+  if (!want_dia) {
+    CK(ctx->w_cnt.ensure((size_t)(n + 1) * sizeof(int)));
+    CK(ctx->o_indptr.ensure((size_t)(n + 1) * sizeof(int)));
+    int* mx = flags + FLAG_COUNT - 1;
+    CK(cudaMemsetAsync(mx, 0, sizeof(int), ctx->stream));
+    LAUNCH(ctx, k_offdiag_count, grid_for(n, 256), 256, 0, indptr, ctx->sys_diagpos.as<int>(), n,
+           ctx->w_cnt.as<int>(), mx);
+    int64_t onnz = 0;
+    RET(b200_scan_exclusive_i32(ctx, ctx->w_cnt.as<int>(), ctx->o_indptr.as<int>(), n, &onnz));
+    int maxrow = 0;
+    CK(cudaMemcpy(&maxrow, mx, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(ctx->o_cols.ensure((size_t)(onnz + 2) * sizeof(int)));
+    CK(ctx->o_vals.ensure((size_t)(onnz + 2) * sizeof(double)));
+    LAUNCH(ctx, k_offdiag_emit, grid_for(n, 128), 128, 0, indptr, indices, data, n,
+           ctx->row_begin, s_owned, ctx->o_indptr.as<int>(), ctx->o_cols.as<int>(),
+           ctx->o_vals.as<double>());
+    ctx->o_nnz = onnz;
+    ctx->o_maxrow = maxrow;
+    const int64_t work = onnz + n;
+    ctx->o_nblocks = (work + CSR_Q - 1) / CSR_Q;
+    CK(ctx->o_rowstart.ensure((size_t)(ctx->o_nblocks + 1) * sizeof(int)));
+    LAUNCH(ctx, k_rowstart, (int)((ctx->o_nblocks + 1 + 255) / 256), 256, 0,
+           ctx->o_indptr.as<int>(), n, (int64_t)CSR_Q, ctx->o_nblocks, ctx->o_rowstart.as<int>());
+    ctx->fmt = B200_FMT_CSR;
+  }
+  CK(cudaGetLastError());
+  ctx->op_epoch = ctx->sys_epoch;
+  ctx->stats.fmt = ctx->fmt;
+  ctx->stats.ndiags = ctx->fmt == B200_FMT_DIA ? ctx->dia.nd : 0;
+  return B200_OK;
+}
+
+extern "C" int b200_pcg_prepare(b200_ctx* ctx, int force_format) {
+  if (!ctx || !ctx->have_sys) {
+    if (ctx) ctx->err = "pcg_prepare: no system matrix";
+    return B200_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  if (force_format != ctx->force_fmt) ctx->op_epoch = ~0ull;
+  ctx->force_fmt = force_format;
+  if (ctx->op_epoch == ctx->sys_epoch && ctx->lin_valid) return B200_OK;
+  return prepare_operator(ctx);
+}
+
+extern "C" int b200_set_format(b200_ctx* ctx, int force_format) {
+  if (!ctx || force_format < 0 || force_format > B200_FMT_DIA) return B200_ERR_ARG;
+  if (force_format != ctx->force_fmt) ctx->op_epoch = ~0ull;
+  ctx->force_fmt = force_format;
+  return B200_OK;
+}
+
+extern "C" int b200_pcg_format(b200_ctx* ctx, int* fmt, int* ndiags) {
+  if (!ctx) return B200_ERR_ARG;
+  if (fmt) *fmt = ctx->fmt;
+  if (ndiags) *ndiags = ctx->fmt == B200_FMT_DIA ? ctx->dia.nd : 0;
+  return B200_OK;
+}
+
+// ======================================================= K4: the PCG kernels
+// All kernels read their scalars (alpha/beta ingredients) from device memory;
+// the host never sits between two iterations.
+
+// ---- K_A (DIA): Ap = A~ p, partial p.Ap.  One row per thread, every load
+// coalesced; the 2*ND neighbour reads of p and the second read of each v_m hit
+// L1/L2 (re-use distance <= k_max rows).
+template <int ND, bool UNIT>
+__global__ void __launch_bounds__(PCG_T) k_dia_spmv_dot(DiaPack A, const double* __restrict__ p,
+                                                        const double* __restrict__ dexp,
+                                                        double* __restrict__ ap, int64_t n,
+                                                        double* part, unsigned* ticket,
+                                                        double* out_pap) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double dot = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double pi = p[i];
+    double acc = UNIT ? pi : dexp[i] * pi;
+#pragma unroll
+    for (int m = 0; m < ND; ++m) {
+      const int64_t k = A.off[m];
+      acc += A.v[m][i] * p[i + k];
+      acc += A.v[m][i - k] * p[i - k];
+    }
+    ap[i] = acc;
+    dot += pi * acc;
+  }
+  double v[1] = {dot};
+  double* o[1] = {out_pap};
+  grid_sum_finalize<1>(v, part, ticket, o);
+}
+
+// ---- K_A (CSR-stream): vals/cols streamed coalesced into shared memory as
+// products, then one thread per row adds its segment.
+template <bool UNIT>
+__global__ void __launch_bounds__(PCG_T) k_csr_stream_spmv_dot(
+    const int* __restrict__ optr, const int* __restrict__ ocols, const double* __restrict__ ovals,
+    const int* __restrict__ rowstart, const double* __restrict__ p, const double* __restrict__ dexp,
+    double* __restrict__ ap, double* part, unsigned* ticket, double* out_pap) {
+  extern __shared__ double prod[];
+  double dot = 0.0;
+  const int r0 = rowstart[blockIdx.x], r1 = rowstart[blockIdx.x + 1];
+  if (r1 > r0) {
+    const int e0 = optr[r0], e1 = optr[r1];
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) prod[e - e0] = ovals[e] * p[ocols[e]];
+    __syncthreads();
+    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+      const double pi = p[r];
+      double acc = UNIT ? pi : dexp[r] * pi;
+      const int b = optr[r] - e0, e = optr[r + 1] - e0;
+      for (int k = b; k < e; ++k) acc += prod[k];
+      ap[r] = acc;
+      dot += pi * acc;
+    }
+  }
+  double v[1] = {dot};
+  double* o[1] = {out_pap};
+  grid_sum_finalize<1>(v, part, ticket, o);
+}
+
+// fallback for matrices with very long rows: one warp per row
+template <bool UNIT>
+__global__ void __launch_bounds__(PCG_T) k_csr_warp_spmv_dot(
+    const int* __restrict__ optr, const int* __restrict__ ocols, const double* __restrict__ ovals,
+    const double* __restrict__ p, const double* __restrict__ dexp, double* __restrict__ ap,
+    int64_t n, double* part, unsigned* ticket, double* out_pap) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double dot = 0.0;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += wstride) {
+    double s = 0.0;
+    for (int e = optr[r] + lane; e < optr[r + 1]; e += 32) s += ovals[e] * p[ocols[e]];
+    s = warp_sum(s);
+    if (lane == 0) {
+      const double pi = p[r];
+      s += UNIT ? pi : dexp[r] * pi;
+      ap[r] = s;
+      dot += pi * s;
+    }
+  }
+  double v[1] = {dot};
+  double* o[1] = {out_pap};
+  grid_sum_finalize<1>(v, part, ticket, o);
+}
+
+// ---- K_B: x += alpha p ; r -= alpha Ap ; rr' = r.r  (and sum d r^2 when asked)
+template <bool TRUE_NORM>
+__global__ void __launch_bounds__(PCG_T) k_update_xr(double* __restrict__ x, double* __restrict__ r,
+                                                     const double* __restrict__ p,
+                                                     const double* __restrict__ ap,
+                                                     const double* __restrict__ diag, int64_t n,
+                                                     const double* __restrict__ sc, int rr_in,
+                                                     int rr_out, double* part, unsigned* ticket,
+                                                     double* scw) {
+  const double rr = sc[rr_in], pap = sc[SC_PAP];
+  const double alpha = (pap > 0.0 || pap < 0.0) ? rr / pap : 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double s = 0.0, t = 0.0;
+  const int64_t n2 = n >> 1;
+  double2* x2 = reinterpret_cast<double2*>(x);
+  double2* r2 = reinterpret_cast<double2*>(r);
+  const double2* p2 = reinterpret_cast<const double2*>(p);
+  const double2* a2 = reinterpret_cast<const double2*>(ap);
+  const double2* d2 = reinterpret_cast<const double2*>(diag);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    double2 xv = x2[i], rv = r2[i];
+    const double2 pv = p2[i], av = a2[i];
+    xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+    rv.x -= alpha * av.x; rv.y -= alpha * av.y;
+    x2[i] = xv; r2[i] = rv;
+    s += rv.x * rv.x + rv.y * rv.y;
+    if (TRUE_NORM) { const double2 dv = d2[i]; t += dv.x * rv.x * rv.x + dv.y * rv.y * rv.y; }
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t i = n - 1;
+    const double xn = x[i] + alpha * p[i], rn = r[i] - alpha * ap[i];
+    x[i] = xn; r[i] = rn;
+    s += rn * rn;
+    if (TRUE_NORM) t += diag[i] * rn * rn;
+  }
+  if (TRUE_NORM) {
+    double v[2] = {s, t};
+    double* o[2] = {scw + rr_out, scw + rr_out + 1};
+    grid_sum_finalize<2>(v, part, ticket, o);
+  } else {
+    double v[1] = {s};
+    double* o[1] = {scw + rr_out};
+    grid_sum_finalize<1>(v, part, ticket, o);
+  }
+}
+
+// ---- K_C: p = r + beta p
+__global__ void __launch_bounds__(PCG_T) k_update_p(double* __restrict__ p,
+                                                    const double* __restrict__ r, int64_t n,
+                                                    const double* __restrict__ sc, int rr_old,
+                                                    int rr_new) {
+  const double ro = sc[rr_old], rn = sc[rr_new];
+  const double beta = (ro > 0.0) ? rn / ro : 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n2 = n >> 1;
+  double2* p2 = reinterpret_cast<double2*>(p);
+  const double2* r2 = reinterpret_cast<const double2*>(r);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    double2 pv = p2[i];
+    const double2 rv = r2[i];
+    pv.x = rv.x + beta * pv.x; pv.y = rv.y + beta * pv.y;
+    p2[i] = pv;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = r[n - 1] + beta * p[n - 1];
+}
+
+// ---- setup / teardown kernels
+// xt = sqrt(d) x0 (or the exact value on singleton rows), bt = s b, |b|^2
+__global__ void __launch_bounds__(PCG_T) k_pcg_init(const double* __restrict__ x0,
+                                                    const double* __restrict__ b,
+                                                    const double* __restrict__ s,
+                                                    const int* __restrict__ sys_indptr,
+                                                    const int* __restrict__ diagpos, int unit,
+                                                    const double* __restrict__ dexp,
+                                                    double* __restrict__ xt, double* __restrict__ bt,
+                                                    int64_t n, double* part, unsigned* ticket,
+                                                    double* out_b2, int* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double b2 = 0.0;
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double bi = b[i], si = s[i];
+    const double bti = si * bi;
+    bt[i] = bti;
+    b2 += bi * bi;
+    const bool singleton = (sys_indptr[i + 1] - sys_indptr[i] == 1) && diagpos[i] >= 0;
+    double x = x0 ? x0[i] / si : 0.0;
+    if (!isfinite(x) || !isfinite(bi)) bad = true;
+    if (singleton) x = unit ? bti : ((dexp[i] != 0.0) ? bti / dexp[i] : x);
+    xt[i] = x;
+  }
+  if (bad) flags[FLAG_NONFINITE] = 1;
+  double v[1] = {b2};
+  double* o[1] = {out_b2};
+  grid_sum_finalize<1>(v, part, ticket, o);
+}
+
+// r = bt - ap ; p = r ; rr = r.r ; true = sum d r^2
+__global__ void __launch_bounds__(PCG_T) k_pcg_resid(const double* __restrict__ bt,
+                                                     const double* __restrict__ ap,
+                                                     const double* __restrict__ diag,
+                                                     double* __restrict__ r, double* __restrict__ p,
+                                                     int64_t n, double* part, unsigned* ticket,
+                                                     double* out_rr, double* out_true) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double s = 0.0, t = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double ri = bt[i] - ap[i];
+    r[i] = ri;
+    p[i] = ri;
+    s += ri * ri;
+    t += diag[i] * ri * ri;
+  }
+  double v[2] = {s, t};
+  double* o[2] = {out_rr, out_true};
+  grid_sum_finalize<2>(v, part, ticket, o);
+}
+
+__global__ void __launch_bounds__(PCG_T) k_pcg_final(const double* __restrict__ xt,
+                                                     const double* __restrict__ s,
+                                                     double* __restrict__ x, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    x[i] = s[i] * xt[i];
+}
+
+__global__ void k_fill_const(double* a, int64_t n, double v) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] = v;
+}
+
+// --------------------------------------------------------------- launchers
+static int pcg_grid(b200_ctx* ctx, int per_thread) {
+  // persistent-style grid: a multiple of the SM count, grid-stride inside
+  int64_t want = (ctx->n + (int64_t)PCG_T * per_thread - 1) / ((int64_t)PCG_T * per_thread);
+  const int64_t cap = 148 * 8;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+static int launch_spmv_dot(b200_ctx* ctx, const double* p_owned, double* ap_owned, double* out) {
+  double* part = ctx->w_part.as<double>();
+  unsigned* ticket = ctx->w_ticket.as<unsigned>();
+  const double* dexp = ctx->dexp.as<double>();
+  const int64_t n = ctx->n;
+  if (ctx->fmt == B200_FMT_DIA) {
+    const int g = pcg_grid(ctx, 1);
+#define DIA_CASE(ND)                                                                       \
+  case ND:                                                                                 \
+    LAUNCH(ctx, (k_dia_spmv_dot<ND, true>), g, PCG_T, 0, ctx->dia, p_owned, dexp, ap_owned, n, \
+           part, ticket, out);                                                             \
+    break;
+    switch (ctx->dia.nd) {
+      DIA_CASE(1) DIA_CASE(2) DIA_CASE(3) DIA_CASE(4) DIA_CASE(5) DIA_CASE(6) DIA_CASE(7)
+      DIA_CASE(8)
+      default: FAIL(B200_ERR_ARG, "bad diagonal count");
+    }
+#undef DIA_CASE
+  } else if (ctx->o_maxrow <= CSR_MAXROW) {
+    const size_t smem = (size_t)(CSR_Q + ctx->o_maxrow + 1) * sizeof(double);
+    if (ctx->unit_diag)
+      LAUNCH(ctx, k_csr_stream_spmv_dot<true>, (int)ctx->o_nblocks, PCG_T, smem,
+             ctx->o_indptr.as<int>(), ctx->o_cols.as<int>(), ctx->o_vals.as<double>(),
+             ctx->o_rowstart.as<int>(), p_owned, dexp, ap_owned, part, ticket, out);
+    else
+      LAUNCH(ctx, k_csr_stream_spmv_dot<false>, (int)ctx->o_nblocks, PCG_T, smem,
+             ctx->o_indptr.as<int>(), ctx->o_cols.as<int>(), ctx->o_vals.as<double>(),
+             ctx->o_rowstart.as<int>(), p_owned, dexp, ap_owned, part, ticket, out);
+  } else {
+    const int g = grid_for(n * 32, PCG_T);
+    if (ctx->unit_diag)
+      LAUNCH(ctx, k_csr_warp_spmv_dot<true>, g, PCG_T, 0, ctx->o_indptr.as<int>(),
+             ctx->o_cols.as<int>(), ctx->o_vals.as<double>(), p_owned, dexp, ap_owned, n, part,
+             ticket, out);
+    else
+      LAUNCH(ctx, k_csr_warp_spmv_dot<false>, g, PCG_T, 0, ctx->o_indptr.as<int>(),
+             ctx->o_cols.as<int>(), ctx->o_vals.as<double>(), p_owned, dexp, ap_owned, n, part,
+             ticket, out);
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol,
+                        int64_t maxiter, double* x, int64_t* iters, double* relres, int* info) {
+  if (!ctx || !ctx->have_sys || !x) {
+    if (ctx) ctx->err = "pcg: no system matrix / null output";
+    return B200_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  RET(b200_pcg_prepare(ctx, ctx->force_fmt));
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  const int64_t n = ctx->n, pad = ctx->pad;
+  if (maxiter <= 0) maxiter = 10 * ctx->n_global;
+  double* sc = ctx->scal.as<double>();
+  double* part = ctx->w_part.as<double>();
+  unsigned* ticket = ctx->w_ticket.as<unsigned>();
+  int* flags = ctx->w_flags.as<int>();
+  double* xt = owned(ctx->vx, pad);
+  double* r = owned(ctx->vr, pad);
+  double* p = owned(ctx->vp, pad);
+  double* ap = owned(ctx->vap, pad);
+  double* bt = owned(ctx->vb, pad);
+  const double* s = owned(ctx->sc, pad);
+  const double* d = cur_diag(ctx);
+  const int g2 = pcg_grid(ctx, 2);
+  const int g1 = pcg_grid(ctx, 1);
+  const bool multi = ctx->nranks > 1;
+
+  CK(cudaMemsetAsync(flags, 0, FLAG_COUNT * sizeof(int), ctx->stream));
+  CK(cudaMemsetAsync(sc, 0, SC_COUNT * sizeof(double), ctx->stream));
+  LAUNCH(ctx, k_pcg_init, g1, PCG_T, 0, x0, cur_b(ctx), s, ctx->sys_indptr.as<int>(),
+         ctx->sys_diagpos.as<int>(), ctx->unit_diag ? 1 : 0, ctx->dexp.as<double>(), xt, bt, n,
+         part, ticket, sc + SC_BNORM, flags);
+  if (!ctx->unit_diag) {
+    // no scaling was applied: the recurrence residual already is the true one
+    CK(ctx->w_tmp1.ensure((size_t)n * sizeof(double)));
+    LAUNCH(ctx, k_fill_const, g1, PCG_T, 0, ctx->w_tmp1.as<double>(), n, 1.0);
+    d = ctx->w_tmp1.as<double>();
+  }
+  if (multi) {
+    RET(b200_allreduce_sum(ctx, sc + SC_BNORM, 1));
+    RET(b200_halo_exchange(ctx, ctx->vx.as<double>()));
+  }
+  RET(launch_spmv_dot(ctx, xt, ap, sc + SC_AUX2));
+  LAUNCH(ctx, k_pcg_resid, g1, PCG_T, 0, bt, ap, d, r, p, n, part, ticket, sc + SC_RR0,
+         sc + SC_TRUE0);
+  if (multi) RET(b200_allreduce_sum(ctx, sc + SC_RR0, 2));
+  CK(cudaMemcpyAsync(ctx->scal_h, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  CK(cudaMemcpyAsync(ctx->flags_h, flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->flags_h[FLAG_NONFINITE]) FAIL(B200_ERR_NONFINITE, "b or x0 contains inf/nan values");
+
+  const double bnorm2 = ctx->scal_h[SC_BNORM];
+  double tol2 = rtol * rtol * bnorm2;
+  if (atol * atol > tol2) tol2 = atol * atol;
+  double true2 = ctx->scal_h[SC_TRUE0];
+  int64_t it = 0;
+  int inf = 0;
+  int restarts = 0;
+  if (bnorm2 == 0.0) {
+    // scipy.sparse.linalg.cg returns b (zeros) at once for a zero rhs
+    CK(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.cg_iters = 0;
+    ctx->stats.relres = 0.0;
+    if (iters) *iters = 0;
+    if (relres) *relres = 0.0;
+    if (info) *info = 0;
+    return B200_OK;
+  }
+
+  int batch = 8;
+  double prev_true2 = true2;
+  bool done = !(true2 > tol2);
+  while (!done) {
+    if (it >= maxiter) break;
+    int64_t todo = batch;
+    if (it + todo > maxiter) todo = maxiter - it;
+    for (int64_t k = 0; k < todo; ++k, ++it) {
+      const int in = 2 * (int)(it & 1), out = 2 - in;
+      if (multi) RET(b200_halo_exchange(ctx, ctx->vp.as<double>()));
+      RET(launch_spmv_dot(ctx, p, ap, sc + SC_PAP));
+      if (multi) RET(b200_allreduce_sum(ctx, sc + SC_PAP, 1));
+      if (k == todo - 1) {
+        LAUNCH(ctx, k_update_xr<true>, g2, PCG_T, 0, xt, r, p, ap, d, n, sc, in, out, part, ticket,
+               sc);
+        if (multi) RET(b200_allreduce_sum(ctx, sc + out, 2));
+      } else {
+        LAUNCH(ctx, k_update_xr<false>, g2, PCG_T, 0, xt, r, p, ap, d, n, sc, in, out, part,
+               ticket, sc);
+        if (multi) RET(b200_allreduce_sum(ctx, sc + out, 1));
+      }
+      LAUNCH(ctx, k_update_p, g2, PCG_T, 0, p, r, n, sc, in, out);
+    }
+    const int cur = 2 * (int)(it & 1);      // pair written by the last K_B
+    CK(cudaMemcpyAsync(ctx->scal_h, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    true2 = ctx->scal_h[cur + 1];
+    const double pap = ctx->scal_h[SC_PAP];
+    const double rrn = ctx->scal_h[cur];
+    if (!isfinite(true2) || !isfinite(pap) || !isfinite(rrn)) { inf = -1; break; }
+    if (rrn > 0.0 && !(pap > 0.0)) { inf = -1; break; }   // not SPD: breakdown
+    if (true2 <= tol2) {
+      // confirm with the explicitly recomputed residual (guards against drift
+      // of the recurrence); r and p restart from it if it disagrees
+      if (multi) RET(b200_halo_exchange(ctx, ctx->vx.as<double>()));
+      RET(launch_spmv_dot(ctx, xt, ap, sc + SC_AUX2));
+      LAUNCH(ctx, k_pcg_resid, g1, PCG_T, 0, bt, ap, d, r, p, n, part, ticket, sc + cur,
+             sc + cur + 1);
+      if (multi) RET(b200_allreduce_sum(ctx, sc + cur, 2));
+      CK(cudaMemcpyAsync(ctx->scal_h, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost,
+                         ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      true2 = ctx->scal_h[cur + 1];
+      if (true2 <= tol2 * (1.0 + 1e-6) || restarts >= 4) { done = true; break; }
+      ++restarts;
+      prev_true2 = true2;
+      batch = 8;
+      continue;
+    }
+    // choose the next batch from the observed convergence rate
+    if (true2 < prev_true2 && true2 > 0.0) {
+      const double rate = log(prev_true2 / true2) / (double)todo;   // per iteration
+      const double need = log(true2 / tol2) / rate;
+      int nb = (int)(need * 0.7);
+      if (nb < 4) nb = 4;
+      if (nb > 64) nb = 64;
+      batch = nb;
+    } else {
+      batch = batch < 64 ? batch * 2 : 64;
+    }
+    prev_true2 = true2;
+  }
+  LAUNCH(ctx, k_pcg_final, g1, PCG_T, 0, xt, s, x, n);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev2, ctx->stream));
+  CK(cudaEventSynchronize(ctx->ev2));
+  float ms_setup = 0.f, ms_solve = 0.f;
+  cudaEventElapsedTime(&ms_setup, ctx->ev0, ctx->ev1);
+  cudaEventElapsedTime(&ms_solve, ctx->ev1, ctx->ev2);
+  ctx->stats.t_setup_ms = ms_setup;
+  ctx->stats.t_solve_ms = ms_solve;
+  ctx->stats.cg_iters = it;
+  ctx->stats.n = n;
+  ctx->stats.nnz_system = ctx->sys_nnz;
+  const double rel = sqrt(true2 / bnorm2);
+  ctx->stats.relres = rel;
+  if (!done && inf == 0) inf = (int)(it > 0x7fffffff ? 0x7fffffff : (it > 0 ? it : 1));
+  if (iters) *iters = it;
+  if (relres) *relres = rel;
+  if (info) *info = inf;
+  return B200_OK;
+}

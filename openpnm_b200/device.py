@@ -1,0 +1,277 @@
+"""Device-side session: a `b200_ctx` plus the torch tensors handed to it.
+
+PyTorch is used for exactly three things here: owning device buffers
+(`torch.Tensor.data_ptr()` is what crosses the C-ABI), providing the CUDA
+stream the library enqueues on, and -- in `dist.py` -- torch.distributed
+for the rendezvous.  All arithmetic happens inside libb200pnm.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("openpnm_b200 needs a CUDA device (no CPU fallback)")
+    return torch
+
+
+class Context:
+    """One GPU, one stream, one assembled transport problem."""
+
+    def __init__(self, device=0):
+        torch = _torch()
+        self.lib = _lib.load()
+        self.device = int(device)
+        self.tdev = torch.device("cuda", self.device)
+        self._h = C.c_void_p()
+        rc = self.lib.b200_create(self.device, C.byref(self._h))
+        if rc != 0:
+            raise _lib.B200Error(rc, "b200_create failed (is a CUDA device visible?)")
+        with torch.cuda.device(self.tdev):
+            self.stream = torch.cuda.Stream(device=self.tdev)
+        self._ck(self.lib.b200_set_stream(self._h, C.c_void_p(self.stream.cuda_stream)))
+        self._keep = {}          # tensors the library holds raw pointers to
+        self.n = 0
+        self.row_begin = 0
+
+    # ------------------------------------------------------------ plumbing
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.lib.b200_last_error(self._h)
+            raise _lib.B200Error(rc, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.b200_destroy(self._h)
+            self._h = C.c_void_p()
+        self._keep = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def to_device(self, a, dtype=None):
+        """numpy / tensor -> contiguous device tensor on this context's stream."""
+        torch = _torch()
+        if isinstance(a, torch.Tensor):
+            t = a
+            if dtype is not None and t.dtype != dtype:
+                t = t.to(dtype)
+            if t.device != self.tdev:
+                with torch.cuda.stream(self.stream):
+                    t = t.to(self.tdev, non_blocking=True)
+            return t.contiguous()
+        arr = np.ascontiguousarray(a)
+        t = torch.from_numpy(arr)
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        with torch.cuda.stream(self.stream):
+            return t.to(self.tdev, non_blocking=True)
+
+    def empty(self, n, dtype):
+        torch = _torch()
+        with torch.cuda.stream(self.stream):
+            return torch.empty(int(n), dtype=dtype, device=self.tdev)
+
+    def synchronize(self):
+        self._ck(self.lib.b200_synchronize(self._h))
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
+
+    # ------------------------------------------------------------ assembly
+    def build_laplacian(self, conns, g, Np, row_begin=0, row_end=None):
+        torch = _torch()
+        conns = self.to_device(conns, torch.int64)
+        g = self.to_device(g, torch.float64)
+        Nt = int(g.numel())
+        if conns.numel() != 2 * Nt:
+            raise ValueError("conns must be (Nt, 2)")
+        row_end = int(Np) if row_end is None else int(row_end)
+        nnz = C.c_int64()
+        self._ck(self.lib.b200_build_laplacian(self._h, self._p(conns), self._p(g), int(Np), Nt,
+                                               int(row_begin), row_end, C.byref(nnz)))
+        self._keep["conns"], self._keep["g"] = conns, g
+        self.n = row_end - int(row_begin)
+        self.row_begin = int(row_begin)
+        return nnz.value
+
+    def apply_bcs(self, bc_value=None, bc_rate=None, keep_zero_diag=False):
+        torch = _torch()
+        bv = self.to_device(bc_value, torch.float64) if bc_value is not None else None
+        br = self.to_device(bc_rate, torch.float64) if bc_rate is not None else None
+        f, nnz = C.c_double(), C.c_int64()
+        self._ck(self.lib.b200_apply_bcs(self._h, self._p(bv), self._p(br),
+                                         1 if keep_zero_diag else 0, C.byref(f), C.byref(nnz)))
+        return f.value, nnz.value
+
+    def pure_diag_sum(self):
+        s, c = C.c_double(), C.c_int64()
+        self._ck(self.lib.b200_pure_diag_sum(self._h, C.byref(s), C.byref(c)))
+        return s.value, c.value
+
+    def set_diag_mean(self, f):
+        self._ck(self.lib.b200_set_diag_mean(self._h, float(f)))
+
+    def load_coo(self, row, col, data, n):
+        torch = _torch()
+        row = self.to_device(row, torch.int32)
+        col = self.to_device(col, torch.int32)
+        data = self.to_device(data, torch.float64)
+        nnz = C.c_int64()
+        self._ck(self.lib.b200_load_coo(self._h, self._p(row), self._p(col), self._p(data),
+                                        int(data.numel()), int(n), C.byref(nnz)))
+        self.n = int(n)
+        return nnz.value
+
+    def load_csr(self, indptr, indices, data, n):
+        torch = _torch()
+        indptr = self.to_device(indptr, torch.int32)
+        indices = self.to_device(indices, torch.int32)
+        data = self.to_device(data, torch.float64)
+        self._ck(self.lib.b200_load_csr(self._h, self._p(indptr), self._p(indices), self._p(data),
+                                        int(n), int(data.numel())))
+        self.n = int(n)
+
+    def set_b(self, b):
+        torch = _torch()
+        b = self.to_device(b, torch.float64)
+        self._ck(self.lib.b200_set_b(self._h, self._p(b)))
+
+    def get_b(self):
+        torch = _torch()
+        out = self.empty(self.n, torch.float64)
+        self._ck(self.lib.b200_get_b(self._h, self._p(out)))
+        return out
+
+    def csr_shape(self, which):
+        n, nnz = C.c_int64(), C.c_int64()
+        self._ck(self.lib.b200_csr_shape(self._h, which, C.byref(n), C.byref(nnz)))
+        return n.value, nnz.value
+
+    def export_csr(self, which=_lib.MAT_SYSTEM):
+        """(indptr, indices, data) as device tensors."""
+        torch = _torch()
+        n, nnz = self.csr_shape(which)
+        ip = self.empty(n + 1, torch.int32)
+        ix = self.empty(max(nnz, 1), torch.int32)
+        dt = self.empty(max(nnz, 1), torch.float64)
+        self._ck(self.lib.b200_export_csr(self._h, which, self._p(ip), self._p(ix), self._p(dt)))
+        return ip, ix[:nnz], dt[:nnz]
+
+    def export_csr_scipy(self, which=_lib.MAT_SYSTEM, ncols=None):
+        import scipy.sparse as sprs
+        ip, ix, dt = self.export_csr(which)
+        n = ip.numel() - 1
+        return sprs.csr_matrix((dt.cpu().numpy(), ix.cpu().numpy(), ip.cpu().numpy()),
+                               shape=(n, ncols or n))
+
+    # -------------------------------------------------------------- solve
+    def spmv(self, which, x):
+        torch = _torch()
+        x = self.to_device(x, torch.float64)
+        y = self.empty(self.n, torch.float64)
+        self._ck(self.lib.b200_spmv(self._h, which, self._p(x), self._p(y)))
+        return y
+
+    def set_format(self, fmt=0):
+        self._ck(self.lib.b200_set_format(self._h, int(fmt)))
+
+    def pcg_prepare(self, fmt=0):
+        self._ck(self.lib.b200_pcg_prepare(self._h, int(fmt)))
+
+    def pcg_format(self):
+        f, nd = C.c_int(), C.c_int()
+        self._ck(self.lib.b200_pcg_format(self._h, C.byref(f), C.byref(nd)))
+        return f.value, nd.value
+
+    def pcg(self, x0=None, rtol=1e-8, atol=0.0, maxiter=0, out=None):
+        torch = _torch()
+        x0 = self.to_device(x0, torch.float64) if x0 is not None else None
+        x = out if out is not None else self.empty(self.n, torch.float64)
+        it, rel, info = C.c_int64(), C.c_double(), C.c_int()
+        self._ck(self.lib.b200_pcg(self._h, self._p(x0), float(rtol), float(atol), int(maxiter),
+                                   self._p(x), C.byref(it), C.byref(rel), C.byref(info)))
+        return x, it.value, rel.value, info.value
+
+    def clear_sources(self):
+        self._ck(self.lib.b200_clear_sources(self._h))
+        self._keep["src"] = []
+
+    def add_source(self, kind, mask, p1, p2, p3=None):
+        torch = _torch()
+        n = self.n
+
+        def vec(v):
+            if v is None:
+                return None
+            a = np.asarray(v, dtype=np.float64)
+            if a.ndim == 0:
+                a = np.full(n, float(a))
+            return self.to_device(a, torch.float64)
+
+        m = self.to_device(np.ascontiguousarray(mask, dtype=np.uint8), torch.uint8)
+        t1, t2, t3 = vec(p1), vec(p2), vec(p3)
+        self._ck(self.lib.b200_add_source(self._h, int(kind), self._p(m), self._p(t1),
+                                          self._p(t2), self._p(t3)))
+        self._keep.setdefault("src", []).append((m, t1, t2, t3))
+
+    def picard(self, x0=None, relaxation=1.0, newton_maxiter=5000, f_rtol=1e-6, x_rtol=1e-6,
+               cg_rtol=1e-10, cg_maxiter=0):
+        torch = _torch()
+        x0 = self.to_device(x0, torch.float64) if x0 is not None else None
+        x = self.empty(self.n, torch.float64)
+        ni, conv, cgt, info = C.c_int64(), C.c_int(), C.c_int64(), C.c_int()
+        self._ck(self.lib.b200_picard(self._h, self._p(x0), float(relaxation),
+                                      int(newton_maxiter), float(f_rtol), float(x_rtol),
+                                      float(cg_rtol), int(cg_maxiter), self._p(x), C.byref(ni),
+                                      C.byref(conv), C.byref(cgt), C.byref(info)))
+        return x, ni.value, bool(conv.value), cgt.value, info.value
+
+    def rate_pores(self, x, pores):
+        torch = _torch()
+        x = self.to_device(x, torch.float64)
+        pores = self.to_device(np.ascontiguousarray(pores, dtype=np.int64), torch.int64)
+        out = self.empty(pores.numel(), torch.float64)
+        self._ck(self.lib.b200_rate_pores(self._h, self._p(x), self._p(pores),
+                                          int(pores.numel()), self._p(out)))
+        return out
+
+    def rate_throats(self, x, throats):
+        torch = _torch()
+        x = self.to_device(x, torch.float64)
+        throats = self.to_device(np.ascontiguousarray(throats, dtype=np.int64), torch.int64)
+        out = self.empty(throats.numel(), torch.float64)
+        self._ck(self.lib.b200_rate_throats(self._h, self._p(self._keep["conns"]),
+                                            self._p(self._keep["g"]), self._p(x),
+                                            self._p(throats), int(throats.numel()), self._p(out)))
+        return out
+
+    def stats(self):
+        s = _lib.Stats()
+        self._ck(self.lib.b200_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in _lib.Stats._fields_}
+
+    # ------------------------------------------------- host-buffer entry
+    def solve_coo_host(self, row, col, data, n, b, x0, rtol, atol, maxiter):
+        row = _lib.as_c(row, np.int32)
+        col = _lib.as_c(col, np.int32)
+        data = _lib.as_c(data, np.float64)
+        b = _lib.as_c(b, np.float64)
+        x0 = _lib.as_c(x0, np.float64) if x0 is not None else None
+        x = np.empty(int(n), dtype=np.float64)
+        it, rel, info = C.c_int64(), C.c_double(), C.c_int()
+        self._ck(self.lib.b200_solve_coo_h(
+            self._h, _lib.np_ptr(row), _lib.np_ptr(col), _lib.np_ptr(data), int(data.size),
+            int(n), _lib.np_ptr(b), _lib.np_ptr(x0) if x0 is not None else C.c_void_p(),
+            float(rtol), float(atol), int(maxiter), _lib.np_ptr(x), C.byref(it), C.byref(rel),
+            C.byref(info)))
+        self.n = int(n)
+        return x, it.value, rel.value, info.value

@@ -1,0 +1,197 @@
+"""Minimal host-side containers for the inputs of the transport path.
+
+The B200 algorithms accept either real OpenPNM objects (anything with
+``['throat.conns']``, ``.Np``, ``.Nt``, ``.pores(label)``) or these light
+stand-ins, which exist so the path can be driven on a machine where OpenPNM
+itself is not installed (benchmarks, GPU tests).  Only what the solve reads is
+reproduced: topology arrays and labels.  Geometry models, plotting, I/O, etc.
+stay in OpenPNM.
+"""
+import numpy as np
+
+__all__ = ["Network", "Cubic", "Phase"]
+
+
+class _Store(dict):
+    """dict of numpy arrays with OpenPNM's 'pore.' / 'throat.' key rules
+    (openpnm/core/_base2.py:49-200, the subset the transport path touches):
+    scalars broadcast to Np/Nt-long arrays, nested prefixes readable as dicts."""
+
+    def _count(self, key):
+        raise NotImplementedError
+
+    def __setitem__(self, key, value):
+        n = self._count(key)
+        a = np.asarray(value)
+        if a.ndim == 0 and n is not None:
+            a = np.full(n, a[()])
+        elif n is not None and a.shape[0] != n:
+            raise ValueError(f"{key}: expected first dimension {n}, got {a.shape}")
+        super().__setitem__(key, np.array(a))
+
+    def __getitem__(self, key):
+        try:
+            return super().__getitem__(key)
+        except KeyError:
+            pre = key + "."
+            sub = {k[len(pre):]: v for k, v in self.items() if k.startswith(pre)}
+            if sub:
+                return sub
+            raise
+
+    def __delitem__(self, key):
+        if key in self.keys():
+            return super().__delitem__(key)
+        pre = key + "."
+        hits = [k for k in self.keys() if k.startswith(pre)]
+        if not hits:
+            raise KeyError(key)
+        for k in hits:
+            super().__delitem__(k)
+
+
+class Network(_Store):
+    """Pore coordinates + throat connections (openpnm/network/_network.py)."""
+
+    def __init__(self, coords=None, conns=None, Np=None):
+        super().__init__()
+        conns = np.asarray(conns, dtype=np.int64).reshape(-1, 2)
+        # conns are forced upper-triangular on assignment (_network.py:123-128)
+        conns = np.sort(conns, axis=1)
+        if coords is not None:
+            Np = np.asarray(coords).shape[0]
+        if Np is None:
+            Np = int(conns.max()) + 1 if conns.size else 0
+        self._Np = int(Np)
+        self._Nt = int(conns.shape[0])
+        dict.__setitem__(self, "throat.conns", np.ascontiguousarray(conns))
+        if coords is not None:
+            dict.__setitem__(self, "pore.coords", np.asarray(coords, dtype=float))
+        dict.__setitem__(self, "pore.all", np.ones(self._Np, dtype=bool))
+        dict.__setitem__(self, "throat.all", np.ones(self._Nt, dtype=bool))
+
+    def _count(self, key):
+        if key.startswith("pore."):
+            return self._Np
+        if key.startswith("throat."):
+            return self._Nt
+        raise KeyError("keys must start with 'pore.' or 'throat.'")
+
+    @property
+    def Np(self):
+        return self._Np
+
+    @property
+    def Nt(self):
+        return self._Nt
+
+    @property
+    def Ps(self):
+        return np.arange(self._Np)
+
+    @property
+    def Ts(self):
+        return np.arange(self._Nt)
+
+    def pores(self, labels="all"):
+        if isinstance(labels, str):
+            labels = [labels]
+        mask = np.zeros(self._Np, dtype=bool)
+        for lbl in labels:
+            mask |= np.asarray(dict.__getitem__(self, "pore." + lbl.split("pore.")[-1]), dtype=bool)
+        return np.flatnonzero(mask)
+
+    def throats(self, labels="all"):
+        if isinstance(labels, str):
+            labels = [labels]
+        mask = np.zeros(self._Nt, dtype=bool)
+        for lbl in labels:
+            mask |= np.asarray(dict.__getitem__(self, "throat." + lbl.split("throat.")[-1]),
+                               dtype=bool)
+        return np.flatnonzero(mask)
+
+    @property
+    def conns(self):
+        return dict.__getitem__(self, "throat.conns")
+
+
+class Cubic(Network):
+    """Simple cubic lattice numbered exactly like `op.network.Cubic`.
+
+    Pore index = x*Ny*Nz + y*Nz + z (openpnm/_skgraph/generators/_cubic.py:33-36);
+    throats are the z-, then y-, then x-neighbour pairs (:40-42, 69-73); face
+    labels left/right (x), front/back (y), bottom/top (z) and the xmin/xmax...
+    aliases (_skgraph/generators/tools/_funcs.py:216-250)."""
+
+    def __init__(self, shape, spacing=1.0, coords=True):
+        shape = np.array(shape, ndmin=1, dtype=int)
+        if shape.size < 3:
+            shape = np.concatenate((shape, np.ones(3 - shape.size, dtype=int)))
+        nx, ny, nz = (int(s) for s in shape)
+        n = nx * ny * nz
+        idx = np.arange(n, dtype=np.int64).reshape(nx, ny, nz)
+        tails = np.concatenate((idx[:, :, :-1].ravel(), idx[:, :-1, :].ravel(),
+                                idx[:-1, :, :].ravel()))
+        heads = np.concatenate((idx[:, :, 1:].ravel(), idx[:, 1:, :].ravel(),
+                                idx[1:, :, :].ravel()))
+        conns = np.empty((tails.size, 2), dtype=np.int64)
+        conns[:, 0] = tails
+        conns[:, 1] = heads
+        del tails, heads, idx
+        super().__init__(coords=None, conns=conns, Np=n)
+        self.shape = (nx, ny, nz)
+        self.spacing = np.ones(3) * np.asarray(spacing, dtype=float)
+        if coords:
+            ii, jj, kk = np.unravel_index(np.arange(n), (nx, ny, nz))
+            c = (np.vstack((ii, jj, kk)).T + 0.5) * self.spacing
+            dict.__setitem__(self, "pore.coords", c)
+
+    def _face(self, axis, last):
+        nx, ny, nz = self.shape
+        idx = np.arange(self._Np, dtype=np.int64).reshape(nx, ny, nz)
+        sl = [slice(None)] * 3
+        sl[axis] = -1 if last else 0
+        return np.sort(idx[tuple(sl)].ravel())
+
+    _FACES = {"left": (0, False), "right": (0, True), "front": (1, False), "back": (1, True),
+              "bottom": (2, False), "top": (2, True), "xmin": (0, False), "xmax": (0, True),
+              "ymin": (1, False), "ymax": (1, True), "zmin": (2, False), "zmax": (2, True)}
+
+    def pores(self, labels="all"):
+        if isinstance(labels, str):
+            labels = [labels]
+        out = []
+        rest = []
+        for lbl in labels:
+            key = lbl.split("pore.")[-1]
+            if key in self._FACES and ("pore." + key) not in self.keys():
+                out.append(self._face(*self._FACES[key]))
+            else:
+                rest.append(lbl)
+        if rest:
+            out.append(super().pores(rest))
+        return np.unique(np.concatenate(out)) if out else np.array([], dtype=np.int64)
+
+
+class Phase(_Store):
+    """Bag of pore/throat properties bound to a network (openpnm/phase/_phase.py)."""
+
+    def __init__(self, network, name="phase_01"):
+        super().__init__()
+        self.network = network
+        self.name = name
+        self.models = {}
+
+    def add_model(self, propname, model, **kwargs):
+        """Register a pore-scale model the way `phase.add_model` does
+        (openpnm/core/_models.py): only the source-term models are evaluated
+        by this package (on the device); `model` is the function or its name."""
+        kwargs.pop("regen_mode", None)
+        self.models[propname] = dict(model=model, **kwargs)
+
+    def _count(self, key):
+        if key.startswith("pore."):
+            return self.network.Np
+        if key.startswith("throat."):
+            return self.network.Nt
+        raise KeyError("keys must start with 'pore.' or 'throat.'")

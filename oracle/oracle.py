@@ -1,0 +1,367 @@
+"""CPU oracle for the OpenPNM transport-solve hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a numpy/scipy *restatement* of the reference algorithm.  It is the
+checker for the CUDA path, never the thing shipped or measured as the product:
+only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` /
+`--impl reference` legs may import it.  `openpnm_b200/` must never import it.
+
+Parity status: PINNED.  `tests/golden/make_golden.py` runs the real reference
+(/root/reference, through `tests/ref_shim.py`) in the build container, checks
+every function below against it, and commits the resulting vectors under
+`tests/golden/`; `tests/test_oracle_golden.py` re-checks the oracle against
+those vectors and against the known-answer constants of the reference's own
+tests (SolversTest, SubclassedTransportTest, GenericTransportTest,
+ReactiveTransportTest, Flow_in_straight_conduit).
+
+Third-party arithmetic the reference delegates to (not vendored, not pinned by
+the reference: setup.py:46-64): scipy (this image: 1.18.1) --
+`scipy.sparse.csgraph.laplacian`, `coo_matrix.tocsr`, `linalg.spsolve`
+(SuperLU), `linalg.cg`, `optimize._nonlin.TerminationCondition`.  scipy is
+present on both the build container and the GPU box, so the oracle calls
+`spsolve`/`tocsr` directly (exactly what openpnm/solvers/_scipy.py:13-15 does) and
+restates the rest in numpy so that each step can be compared separately.
+
+All citations are file:line under /root/reference/.
+"""
+import numpy as np
+import scipy.sparse as sprs
+import scipy.sparse.linalg as spla
+
+__all__ = [
+    "cubic_network", "adjacency_coo", "laplacian_coo", "build_A", "apply_bcs",
+    "apply_sources", "to_csr", "source_term", "picard_run", "rate",
+    "jacobi_pcg", "spsolve", "transport_run", "delaunay_network",
+]
+
+
+# --------------------------------------------------------------------------
+# network generation (input side; openpnm/_skgraph/generators/_cubic.py:25-82)
+# --------------------------------------------------------------------------
+def cubic_network(shape, spacing=1.0):
+    """Cubic lattice exactly as `op.network.Cubic(shape, spacing)` numbers it.
+
+    Pore index = x*Ny*Nz + y*Nz + z (z fastest; _cubic.py:33-36); throats are
+    the z-neighbour pairs, then y-, then x- (_cubic.py:40-42, 69-73); conns are
+    int64, [low, high].  Face labels follow
+    _skgraph/generators/tools/_funcs.py:216-250: left/right = x min/max,
+    front/back = y min/max, bottom/top = z min/max.
+    """
+    shape = np.array(shape, ndmin=1, dtype=int)
+    if shape.size < 3:
+        shape = np.concatenate((shape, np.ones(3 - shape.size, dtype=int)))
+    nx, ny, nz = (int(s) for s in shape)
+    idx = np.arange(nx * ny * nz, dtype=np.int64).reshape(nx, ny, nz)
+    tails = [idx[:, :, :-1].ravel(), idx[:, :-1, :].ravel(), idx[:-1, :, :].ravel()]
+    heads = [idx[:, :, 1:].ravel(), idx[:, 1:, :].ravel(), idx[1:, :, :].ravel()]
+    conns = np.vstack((np.concatenate(tails), np.concatenate(heads))).T
+    conns = np.ascontiguousarray(conns, dtype=np.int64)
+    sp = np.ones(3) * np.asarray(spacing, dtype=float)
+    ii, jj, kk = np.unravel_index(np.arange(nx * ny * nz), (nx, ny, nz))
+    coords = (np.vstack((ii, jj, kk)).T + 0.5) * sp
+    labels = {
+        "left": np.flatnonzero(ii == 0), "right": np.flatnonzero(ii == nx - 1),
+        "front": np.flatnonzero(jj == 0), "back": np.flatnonzero(jj == ny - 1),
+        "bottom": np.flatnonzero(kk == 0), "top": np.flatnonzero(kk == nz - 1),
+    }
+    return {"shape": (nx, ny, nz), "Np": nx * ny * nz, "Nt": conns.shape[0],
+            "conns": conns, "coords": coords, "labels": labels}
+
+
+def delaunay_network(points):
+    """Delaunay edges of `points` as upper-triangular, de-duplicated conns.
+
+    Same edge set as `tri_to_am` (_skgraph/tools/_funcs.py:629-669) followed by
+    the triu + coo conversion in `generators.delaunay` (_delaunay.py:8-59), but
+    built from `vertex_neighbor_vertices` without the per-point Python loop.
+    """
+    import scipy.spatial as sptl
+    tri = sptl.Delaunay(points)
+    indptr, indices = tri.vertex_neighbor_vertices
+    rows = np.repeat(np.arange(points.shape[0]), np.diff(indptr))
+    keep = rows < indices
+    conns = np.vstack((rows[keep], indices[keep])).T.astype(np.int64)
+    order = np.lexsort((conns[:, 1], conns[:, 0]))
+    return np.ascontiguousarray(conns[order])
+
+
+# --------------------------------------------------------------------------
+# assembly
+# --------------------------------------------------------------------------
+def adjacency_coo(conns, g, Np):
+    """`Network.create_adjacency_matrix(weights=g, fmt='coo')`, symmetric branch.
+
+    openpnm/network/_network.py:274-293: row=[c0;c1], col=[c1;c0], data=[g;g].
+    """
+    conns = np.asarray(conns)
+    g = np.asarray(g, dtype=float)
+    row = np.append(conns[:, 0], conns[:, 1])
+    col = np.append(conns[:, 1], conns[:, 0])
+    data = np.append(g, g)
+    return row, col, data
+
+
+def laplacian_coo(row, col, data, Np):
+    """`scipy.sparse.csgraph.laplacian(am)` on a COO adjacency, in numpy.
+
+    scipy/sparse/csgraph/_laplacian.py:449-484 (`_laplacian_sparse`):
+    w = colsum - diagonal; data *= -1; COO `setdiag(w)` drops every existing
+    diagonal entry and appends (i, i, w_i) for i = 0..Np-1 (_coo.py:511-547).
+    """
+    colsum = np.zeros(Np)
+    np.add.at(colsum, col, data)
+    dmask = row == col
+    diag = np.zeros(Np)
+    np.add.at(diag, row[dmask], data[dmask])
+    w = colsum - diag
+    keep = ~dmask
+    ar = np.arange(Np, dtype=row.dtype)
+    return (np.concatenate((row[keep], ar)),
+            np.concatenate((col[keep], ar)),
+            np.concatenate((-data[keep], w)))
+
+
+def build_A(conns, g, Np):
+    """`Transport._build_A` (openpnm/algorithms/_transport.py:95-115) -> COO triple."""
+    row, col, data = adjacency_coo(conns, g, Np)
+    return laplacian_coo(row, col, data, Np)
+
+
+def _coo_diagonal(row, col, data, Np):
+    d = np.zeros(Np)
+    m = row == col
+    np.add.at(d, row[m], data[m])
+    return d
+
+
+def _coo_setdiag(row, col, data, values):
+    keep = row != col
+    ar = np.arange(values.size, dtype=row.dtype)
+    return (np.concatenate((row[keep], ar)), np.concatenate((col[keep], ar)),
+            np.concatenate((data[keep], values)))
+
+
+def apply_bcs(A, Np, bc_value=None, bc_rate=None):
+    """`Transport._build_b` + `_apply_BCs` (_transport.py:117-121, 145-169).
+
+    A is the COO triple of the pure Laplacian.  NaN in bc_value / bc_rate means
+    "no BC here" (Transport.__init__, _transport.py:68-69).  Returns
+    (A_coo_after, b, f).
+    """
+    row, col, data = (np.array(a) for a in A)
+    b = np.zeros(Np)
+    f = np.nan
+    if bc_rate is not None:
+        ind = np.isfinite(bc_rate)
+        b[ind] = bc_rate[ind]
+    if bc_value is not None:
+        f = _coo_diagonal(row, col, data, Np).mean()
+        ind = np.isfinite(bc_value)
+        b[ind] = bc_value[ind] * f
+        x_bc = np.zeros(Np)
+        x_bc[ind] = bc_value[ind]
+        Ax = np.zeros(Np)
+        np.add.at(Ax, row, data * x_bc[col])
+        b[~ind] -= Ax[~ind]
+        mask = ind[row] | ind[col]
+        data[mask] = 0
+        datadiag = _coo_diagonal(row, col, data, Np)
+        datadiag[ind] = f
+        row, col, data = _coo_setdiag(row, col, data, datadiag)
+        nz = data != 0
+        row, col, data = row[nz], col[nz], data[nz]
+    return (row, col, data), b, f
+
+
+def apply_sources(A, b, Np, sources):
+    """`ReactiveTransport._apply_sources` (_reactive_transport.py:125-148).
+
+    sources: iterable of (mask_bool[Np], S1[Np], S2[Np]).
+    """
+    row, col, data = A
+    b = b.copy()
+    for mask, S1, S2 in sources:
+        diag = _coo_diagonal(row, col, data, Np)
+        diag[mask] += -S1[mask]
+        row, col, data = _coo_setdiag(row, col, data, diag)
+        b[mask] += S2[mask]
+    return (row, col, data), b
+
+
+def to_csr(A, Np):
+    """`A.tocsr()` as the solvers do (openpnm/solvers/_scipy.py:13-14)."""
+    row, col, data = A
+    return sprs.coo_matrix((data, (row, col)), shape=(Np, Np)).tocsr()
+
+
+# --------------------------------------------------------------------------
+# source-term models (openpnm/models/physics/source_terms/_funcs.py)
+# --------------------------------------------------------------------------
+def source_term(kind, X, params):
+    """Return (S1, S2, rate) for the three models on the hot path.
+
+    standard_kinetics: _funcs.py:21-69   r = A X^b
+    linear:            _funcs.py:73-116  r = A1 X + A2
+    power_law:         _funcs.py:120-168 r = A1 X^A2 + A3
+    """
+    X = np.asarray(X, dtype=float)
+    with np.errstate(all="ignore"):
+        if kind == "standard_kinetics":
+            A, b = params["prefactor"], params["exponent"]
+            r = A * (X ** b)
+            S1 = A * b * (X ** (b - 1))
+            S2 = A * (1 - b) * (X ** b)
+        elif kind == "linear":
+            A1, A2 = params.get("A1", 0.0), params.get("A2", 0.0)
+            r = A1 * X + A2
+            S1 = A1 * np.ones_like(X)
+            S2 = A2 * np.ones_like(X)
+        elif kind == "power_law":
+            A, B, C = params.get("A1", 0.0), params.get("A2", 0.0), params.get("A3", 0.0)
+            r = A * X ** B + C
+            S1 = A * B * X ** (B - 1)
+            S2 = A * X ** B * (1 - B) + C
+        else:
+            raise ValueError(kind)
+    return S1, S2, r
+
+
+# --------------------------------------------------------------------------
+# solvers
+# --------------------------------------------------------------------------
+def spsolve(A_csr, b):
+    """`ScipySpsolve.solve` (openpnm/solvers/_scipy.py:8-15): SuperLU, exit code 0."""
+    return spla.spsolve(A_csr, b), 0
+
+
+def jacobi_pcg(A_csr, b, x0=None, rtol=1e-8, maxiter=None, precond=True):
+    """Textbook (Jacobi-)preconditioned CG, stop when ||b - A x||_2 <= rtol*||b||_2.
+
+    Same stopping rule as `ScipyCG.solve` (_scipy.py:21-26: tol=self.tol,
+    atol=norm(b)*tol).  Restated in numpy so the iteration count is observable.
+    Returns (x, info, iters) with scipy's info convention (0 ok, >0 maxiter).
+    """
+    n = b.size
+    x = np.zeros(n) if x0 is None else np.array(x0, dtype=float)
+    d = A_csr.diagonal()
+    Minv = 1.0 / d if precond else np.ones(n)
+    if maxiter is None:
+        maxiter = 10 * n
+    atol = rtol * np.linalg.norm(b)
+    r = b - A_csr @ x
+    if np.linalg.norm(r) <= atol:
+        return x, 0, 0
+    z = Minv * r
+    p = z.copy()
+    rz = r @ z
+    for k in range(1, maxiter + 1):
+        Ap = A_csr @ p
+        alpha = rz / (p @ Ap)
+        x += alpha * p
+        r -= alpha * Ap
+        if np.linalg.norm(r) <= atol:
+            return x, 0, k
+        z = Minv * r
+        rz_new = r @ z
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    return x, maxiter, maxiter
+
+
+# --------------------------------------------------------------------------
+# outer loops
+# --------------------------------------------------------------------------
+def _termination_check(state, f, x, dx, f_rtol, x_rtol):
+    """scipy.optimize._nonlin.TerminationCondition.check with f_tol=x_tol=inf,
+    norm=numpy.linalg.norm, as constructed at _reactive_transport.py:183-185."""
+    f_norm, x_norm, dx_norm = (np.linalg.norm(v) for v in (f, x, dx))
+    if state.get("f0") is None:
+        state["f0"] = f_norm
+    if f_norm == 0:
+        return True
+    return bool(f_norm / f_rtol <= state["f0"] and dx_norm / x_rtol <= x_norm)
+
+
+def picard_run(conns, g, Np, bc_value=None, bc_rate=None, sources=(), x0=None,
+               solver=None, relaxation_factor=1.0, newton_maxiter=5000,
+               f_rtol=1e-6, x_rtol=1e-6):
+    """`Transport.run` + `ReactiveTransport._run_special` for one algorithm.
+
+    _transport.py:171-221 and _reactive_transport.py:150-213, including the
+    first-iteration aliasing quirk: `SteadyStateSolution(x0)` is a *view* of x0
+    (_solution.py:17-20) and `xold = self.x` is that buffer, so after the first
+    solve `self.soln[q][:] = self.x` (_transport.py:220) overwrites xold in
+    place and the first `dx = self.x - xold` is identically zero.
+
+    sources: iterable of (mask_bool[Np], kind, params) evaluated at the
+    current x each outer iteration (`_update_iterative_props`,
+    _algorithm.py:69-91).  solver(A_csr, b, x0) -> (x, exit_code).
+    Returns dict(x, num_iter, is_converged, A (COO), b).
+    """
+    if solver is None:
+        solver = lambda A, b, x0: spsolve(A, b)  # noqa: E731
+    pure = build_A(conns, g, Np)
+
+    def update(x):
+        A, b, _ = apply_bcs(pure, Np, bc_value, bc_rate)
+        lin = []
+        for mask, kind, params in sources:
+            S1, S2, _ = source_term(kind, x, params)
+            lin.append((mask, S1, S2))
+        if lin:
+            A, b = apply_sources(A, b, Np, lin)
+        return A, b
+
+    x = np.zeros(Np) if x0 is None else np.array(x0, dtype=float)
+    if not np.isfinite(x).all():
+        raise Exception("x0 contains inf/nan values")
+    w = relaxation_factor
+    A, b = update(x)
+    xold = x
+    dx = np.zeros(Np)
+    state = {}
+    num_iter = 0
+    is_converged = False
+    first = True
+    for i in range(newton_maxiter):
+        res = to_csr(A, Np) @ x - b
+        if _termination_check(state, res, xold, dx, f_rtol, x_rtol):
+            is_converged = True
+            break
+        if not (np.isfinite(A[2]).all() and np.isfinite(b).all()):
+            raise Exception("A or b contains inf/nan values")
+        x_new, exit_code = solver(to_csr(A, Np), b, xold)
+        x = w * x_new + (1 - w) * x
+        A, b = update(x)
+        if first:
+            dx = np.zeros(Np)      # aliasing quirk, see docstring
+            first = False
+        else:
+            dx = x - xold
+        xold = x
+        num_iter = i + 1
+    return {"x": x, "num_iter": num_iter, "is_converged": is_converged,
+            "A": A, "b": b}
+
+
+def transport_run(conns, g, Np, bc_value=None, bc_rate=None, solver=None, x0=None):
+    """Linear problem: one assembly + one solve (what `run` amounts to when
+    there are no sources; num_iter == 1 for a converged direct solve)."""
+    out = picard_run(conns, g, Np, bc_value, bc_rate, (), x0, solver)
+    return out
+
+
+def rate(conns, g, x, pores=None, throats=None, mode="group"):
+    """`Transport.rate` (_transport.py:259-330), always with the pure conductances."""
+    conns = np.asarray(conns)
+    g = np.asarray(g, dtype=float)
+    Qt = g * (x[conns[:, 1]] - x[conns[:, 0]])
+    if throats is not None and np.size(throats):
+        R = np.abs(Qt[np.asarray(throats)])
+    else:
+        Qp = np.zeros(x.size)
+        np.add.at(Qp, conns[:, 0], -Qt)
+        np.add.at(Qp, conns[:, 1], Qt)
+        R = Qp[np.asarray(pores)]
+    if mode == "group":
+        R = np.sum(R)
+    return np.array(R, ndmin=1)

@@ -1,0 +1,396 @@
+"""Generate the golden vectors under tests/golden/ from the REAL reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py [--big]
+
+Every case runs the unmodified reference (imported through tests/ref_shim.py),
+stores inputs + outputs in `tests/golden/<case>.npz`, and at the same time
+checks the oracle restatement (oracle/oracle.py) against the reference's
+output -- this is the step that *pins* the oracle.  `--big` adds the Cubic 50^3
+SuperLU case (~3 minutes of CPU).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+
+import ref_shim  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+op = ref_shim.import_reference()
+assert op is not None, "reference not found"
+META = {}
+
+
+def save(name, **arrays):
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+
+
+def csr_of(alg):
+    A = alg.A.tocsr()
+    A.sort_indices()
+    return A
+
+
+def check_oracle_linear(name, pn, g, bcv, bcr, alg, rtol=1e-9):
+    """Oracle vs reference on the assembled system and the solution."""
+    Np = pn.Np
+    conns = pn["throat.conns"]
+    pure = oracle.build_A(conns, g, Np)
+    A, b, f = oracle.apply_bcs(pure, Np, bcv, bcr)
+    Ao = oracle.to_csr(A, Np)
+    Ar = csr_of(alg)
+    assert np.array_equal(Ao.indptr, Ar.indptr), name
+    assert np.array_equal(Ao.indices, Ar.indices), name
+    assert np.allclose(Ao.data, Ar.data, rtol=1e-13, atol=0), name
+    assert np.allclose(b, alg.b, rtol=1e-12, atol=0), name
+    x, _ = oracle.spsolve(Ao, b)
+    assert np.allclose(x, alg.x, rtol=rtol, atol=0), name
+    return Ao, b, f
+
+
+def linear_case(name, pn, g, value_bcs=(), rate_bcs=(), rate_pores=None,
+                store_full=True, solver=None):
+    ph = op.phase.Phase(network=pn)
+    ph["throat.conductance"] = g
+    alg = op.algorithms.Transport(network=pn, phase=ph)
+    alg.settings._update({"quantity": "pore.x", "conductance": "throat.conductance"})
+    for pores, vals, mode in value_bcs:
+        alg.set_value_BC(pores=pores, values=vals, mode=mode)
+    for pores, vals, mode in rate_bcs:
+        alg.set_rate_BC(pores=pores, rates=vals, mode=mode)
+    t0 = time.time()
+    alg.run(solver=solver or op.solvers.ScipySpsolve())
+    dt = time.time() - t0
+    bcv = np.array(alg["pore.bc.value"], dtype=float)
+    bcr = np.array(alg["pore.bc.rate"], dtype=float)
+    g = np.array(ph["throat.conductance"], dtype=float)
+    Ao, b, f = check_oracle_linear(name, pn, g, bcv, bcr, alg)
+    A = csr_of(alg)
+    out = dict(conns=pn["throat.conns"].astype(np.int64), g=g, bc_value=bcv,
+               bc_rate=bcr, Np=np.int64(pn.Np), f=np.float64(f),
+               b=np.array(alg.b), x=np.array(alg.x),
+               indptr=A.indptr.astype(np.int32), indices=A.indices.astype(np.int32),
+               data=A.data)
+    rates = {}
+    if rate_pores is not None:
+        for lbl, pores in rate_pores.items():
+            r = alg.rate(pores=pores)[0]
+            ro = oracle.rate(pn["throat.conns"], g, np.array(alg.x), pores=pores)[0]
+            assert np.isclose(r, ro, rtol=1e-10, atol=1e-300), (name, lbl, r, ro)
+            rates[lbl] = float(r)
+            out["pores_" + lbl] = np.asarray(pores, dtype=np.int64)
+    if not store_full:
+        for k in ("conns", "g", "indptr", "indices", "data", "b"):
+            out.pop(k)
+    save(name, **out)
+    META[name] = dict(Np=int(pn.Np), Nt=int(pn.Nt), nnz=int(A.nnz), f=float(f),
+                      x_mean=float(np.mean(alg.x)), rates=rates,
+                      num_iter=int(getattr(alg.soln, "num_iter", 1)),
+                      is_converged=bool(alg.soln.is_converged),
+                      ref_seconds=round(dt, 3))
+    print(name, META[name])
+    return alg
+
+
+def g1_solvers():
+    # tests/unit/algorithms/SolversTest.py:12-24
+    pn = op.network.Cubic(shape=[3, 4, 5])
+    g = np.linspace(1, 5, pn.Nt)
+    alg = linear_case("g1_solvers_3x4x5", pn, g,
+                      value_bcs=[(pn.pores("front"), 1.0, "add"),
+                                 (pn.pores("bottom"), 0.0, "overwrite")],
+                      rate_pores={"front": pn.pores("front"), "bottom": pn.pores("bottom")})
+    assert np.isclose(alg.x.mean(), 0.6241341116805926, rtol=1e-12)
+    alg.run(solver=op.solvers.ScipyCG())
+    META["g1_solvers_3x4x5"]["x_mean_scipycg"] = float(alg.x.mean())
+
+
+def g2_stokes():
+    # tests/unit/algorithms/SubclassedTransportTest.py:18-82 (Stokes leg)
+    pn = op.network.Cubic(shape=[9, 9, 9])
+    ph = op.phase.Phase(network=pn)
+    ph["throat.hydraulic_conductance"] = 1.0
+    ph["throat.diffusive_conductance"] = 1.0
+    sf = op.algorithms.StokesFlow(network=pn, phase=ph)
+    sf.set_value_BC(pores=pn.pores("top"), values=101325)
+    sf.set_value_BC(pores=pn.pores("bottom"), values=0)
+    sf.run(solver=op.solvers.ScipySpsolve())
+    r_in = sf.rate(pores=pn.pores("top"))[0]
+    r_out = sf.rate(pores=pn.pores("bottom"))[0]
+    surf = sf.rate(pores=pn.pores("surface"))[0] if "pore.surface" in pn.keys() else np.nan
+    fd = op.algorithms.FickianDiffusion(network=pn, phase=ph)
+    fd.set_value_BC(pores=pn.pores("top"), values=1)
+    fd.set_value_BC(pores=pn.pores("bottom"), values=0)
+    fd.run(solver=op.solvers.ScipySpsolve())
+    r_fd = fd.rate(pores=pn.pores("top"))[0]
+    save("g2_subclassed_9", x_stokes=np.array(sf.x), x_fickian=np.array(fd.x),
+         top=pn.pores("top").astype(np.int64), bottom=pn.pores("bottom").astype(np.int64))
+    META["g2_subclassed_9"] = dict(rate_in_stokes=float(r_in), rate_out_stokes=float(r_out),
+                                   rate_surface=float(surf), rate_in_fickian=float(r_fd),
+                                   num_iter=int(sf.soln.num_iter),
+                                   stokes_quantity=sf.settings["quantity"],
+                                   stokes_conductance=sf.settings["conductance"],
+                                   fickian_quantity=fd.settings["quantity"],
+                                   fickian_conductance=fd.settings["conductance"])
+    print("g2", META["g2_subclassed_9"])
+
+
+def reactive_case(name, shape, g, kind, params, src_label, bc_label, bc_val,
+                  extra_sources=(), x0=None, settings=None):
+    from openpnm.models.physics import source_terms
+    pn = op.network.Cubic(shape=shape)
+    ph = op.phase.Phase(network=pn)
+    if np.isscalar(g):
+        ph["throat.diffusive_conductance"] = g
+    else:
+        ph["throat.diffusive_conductance"] = g(pn) if callable(g) else g
+    srcs = [(src_label, kind, params)] + list(extra_sources)
+    alg = op.algorithms.ReactiveTransport(network=pn, phase=ph)
+    alg.settings._update({"conductance": "throat.diffusive_conductance",
+                          "quantity": "pore.concentration"})
+    if settings:
+        alg.settings._update(settings)
+    out_src = {}
+    for n, (lbl, knd, prm) in enumerate(srcs):
+        kw = {}
+        for k, v in prm.items():
+            key = f"pore.src{n}_{k}"
+            ph[key] = v
+            kw[k] = key
+        ph.add_model(propname=f"pore.reaction{n}", model=getattr(source_terms, knd),
+                     X="pore.concentration", regen_mode="deferred", **kw)
+        pores = pn.pores(lbl) if isinstance(lbl, str) else lbl
+        alg.set_source(pores=pores, propname=f"pore.reaction{n}")
+        out_src[f"src{n}_pores"] = np.asarray(pores, dtype=np.int64)
+    bc_pores = pn.pores(bc_label)
+    alg.set_value_BC(pores=bc_pores, values=bc_val)
+    alg.run(solver=op.solvers.ScipySpsolve(), x0=x0)
+    c = np.array(alg["pore.concentration"])
+    gv = np.array(ph["throat.diffusive_conductance"], dtype=float)
+    # oracle cross-check
+    osrc = []
+    for n, (lbl, knd, prm) in enumerate(srcs):
+        mask = np.zeros(pn.Np, dtype=bool)
+        mask[out_src[f"src{n}_pores"]] = True
+        osrc.append((mask, knd, prm))
+    res = oracle.picard_run(pn["throat.conns"], gv, pn.Np,
+                            bc_value=np.array(alg["pore.bc.value"], dtype=float),
+                            bc_rate=np.array(alg["pore.bc.rate"], dtype=float),
+                            sources=osrc, x0=x0,
+                            relaxation_factor=alg.settings["relaxation_factor"],
+                            newton_maxiter=alg.settings["newton_maxiter"],
+                            f_rtol=alg.settings["f_rtol"], x_rtol=alg.settings["x_rtol"])
+    assert res["num_iter"] == alg.soln.num_iter, (name, res["num_iter"], alg.soln.num_iter)
+    assert res["is_converged"] == alg.soln.is_converged, name
+    if alg.soln.is_converged:
+        assert np.allclose(res["x"], c, rtol=1e-9, atol=0), name
+    Ao = oracle.to_csr(res["A"], pn.Np)
+    Ar = csr_of(alg)
+    assert np.array_equal(Ao.indptr, Ar.indptr) and np.array_equal(Ao.indices, Ar.indices), name
+    r_src = alg.rate(pores=out_src["src0_pores"])[0]
+    save(name, conns=pn["throat.conns"].astype(np.int64), g=gv,
+         bc_value=np.array(alg["pore.bc.value"], dtype=float),
+         bc_rate=np.array(alg["pore.bc.rate"], dtype=float), x=c,
+         x0=np.zeros(pn.Np) if x0 is None else x0,
+         indptr=Ar.indptr.astype(np.int32), indices=Ar.indices.astype(np.int32),
+         data=Ar.data, b=np.array(alg.b), **out_src)
+    META[name] = dict(Np=int(pn.Np), c_mean=float(c.mean()), num_iter=int(alg.soln.num_iter),
+                      is_converged=bool(alg.soln.is_converged), rate_src0=float(r_src),
+                      sources=[dict(kind=k, params={a: float(b) for a, b in p.items()})
+                               for _, k, p in srcs],
+                      settings=dict(relaxation_factor=float(alg.settings["relaxation_factor"]),
+                                    newton_maxiter=int(alg.settings["newton_maxiter"]),
+                                    f_rtol=float(alg.settings["f_rtol"]),
+                                    x_rtol=float(alg.settings["x_rtol"])))
+    print(name, META[name])
+
+
+def g3_reactive():
+    # tests/unit/algorithms/ReactiveTransportTest.py:11-21, 69-77
+    reactive_case("g3_reactive_4_standard_kinetics", [4, 4, 4], 1e-15,
+                  "standard_kinetics", {"prefactor": -1e-15, "exponent": 2},
+                  "bottom", "top", 1.0)
+    assert np.isclose(META["g3_reactive_4_standard_kinetics"]["c_mean"],
+                      0.7171292729553325, rtol=1e-10)
+    reactive_case("g3_reactive_4_power_law", [4, 4, 4], 1e-15,
+                  "power_law", {"A1": -1e-15, "A2": 2, "A3": 0.0},
+                  "bottom", "top", 1.0)
+    reactive_case("g3_reactive_4_linear", [4, 4, 4], 1e-15,
+                  "linear", {"A1": -2e-15, "A2": 1e-16},
+                  "bottom", "top", 1.0)
+    # ReactiveTransportTest.py:97-112: two sources on 'left', value on 'right'
+    reactive_case("g3_reactive_4_two_sources", [4, 4, 4], 1e-15,
+                  "standard_kinetics", {"prefactor": -1e-15, "exponent": 2},
+                  "left", "right", 1.0,
+                  extra_sources=[("left", "standard_kinetics",
+                                  {"prefactor": -1e-15, "exponent": 2})])
+    # ReactiveTransportTest.py:162-174: divergence with relaxation_factor=20
+    reactive_case("g3_reactive_4_diverge", [4, 4, 4], 1e-15,
+                  "standard_kinetics", {"prefactor": -1e-15, "exponent": 2},
+                  "bottom", "top", 1.0,
+                  settings={"relaxation_factor": 20.0, "newton_maxiter": 25})
+    # heterogeneous 10^3 power-law (config 5 in miniature)
+
+    def ghet(pn):
+        return 10.0 ** np.random.default_rng(0).uniform(-15, -12, pn.Nt)
+
+    pn_tmp = op.network.Cubic(shape=[10, 10, 10])
+    interior = np.setdiff1d(pn_tmp.Ps, pn_tmp.pores("left"))
+    reactive_case("g9_reactive_10_power_law", [10, 10, 10], ghet,
+                  "power_law", {"A1": -1e-13, "A2": 2, "A3": 0.0},
+                  interior, "left", 1.0)
+
+
+def g4_csr():
+    # Cubic 4x3x2, g = 1..46, left=2.0 / right=1.0
+    pn = op.network.Cubic(shape=[4, 3, 2])
+    g = np.arange(1, pn.Nt + 1, dtype=float)
+    alg = linear_case("g4_csr_4x3x2", pn, g,
+                      value_bcs=[(pn.pores("left"), 2.0, "add"),
+                                 (pn.pores("right"), 1.0, "add")],
+                      rate_pores={"left": pn.pores("left"), "right": pn.pores("right")})
+    A = csr_of(alg)
+    assert A.nnz == 64
+    assert np.isclose(alg.rate(pores=pn.pores("left"))[0], 73.70713723, rtol=1e-8)
+
+
+def g6_profiles():
+    # tests/unit/algorithms/GenericTransportTest.py:114-135
+    pn = op.network.Cubic(shape=[9, 9, 9])
+    g = np.ones(pn.Nt)
+    a = linear_case("g6_two_values_9", pn, g,
+                    value_bcs=[(pn.pores("top"), 1.0, "add"), (pn.pores("bottom"), 0.0, "add")],
+                    rate_pores={"top": pn.pores("top"), "bottom": pn.pores("bottom")})
+    y = np.unique(np.around(a.x, decimals=3))
+    assert np.allclose(y, np.linspace(0, 1, 9))
+    a = linear_case("g6_value_rate_9", pn, g,
+                    value_bcs=[(pn.pores("top"), 0.0, "add")],
+                    rate_bcs=[(pn.pores("bottom"), 1.0, "add")],
+                    rate_pores={"top": pn.pores("top"), "bottom": pn.pores("bottom")})
+    y = np.unique(np.around(a.x, decimals=3))
+    assert np.allclose(y, np.arange(9.0))
+
+
+def g5_conduit():
+    # tests/integration/Flow_in_straight_conduit.py:8-55 (analytic Hagen-Poiseuille)
+    mu, Pin, Pout = 1.0, 1.0, 0.0
+    rows = []
+    for D in [0.9, 1.0, 1.1, 1.5]:
+        Q = np.pi * (D / 2) ** 4 / (8 * mu * 4) * (Pin - Pout)
+        pn = op.network.Cubic(shape=[5, 1, 1], spacing=1)
+        pn["pore.diameter"] = D
+        pn["throat.diameter"] = D
+        pn.regenerate_models()
+        pn.add_model(propname="throat.hydraulic_size_factors",
+                     model=op.models.geometry.hydraulic_size_factors.spheres_and_cylinders)
+        ph = op.phase.Phase(network=pn)
+        ph["pore.viscosity"] = mu
+        ph.add_model(propname="throat.hydraulic_conductance",
+                     model=op.models.physics.hydraulic_conductance.generic_hydraulic)
+        sf = op.algorithms.StokesFlow(network=pn, phase=ph)
+        sf.set_value_BC(pores=pn.pores("xmin"), values=Pin)
+        sf.set_value_BC(pores=pn.pores("xmax"), values=Pout)
+        sf.run(solver=op.solvers.ScipySpsolve())
+        r = sf.rate(pores=pn.pores("xmin"))[0]
+        assert np.isclose(r, Q, rtol=1e-10)
+        rows.append(dict(D=D, Q=float(Q), rate=float(r),
+                         g=[float(v) for v in ph["throat.hydraulic_conductance"]]))
+    META["g5_conduit"] = rows
+    print("g5", rows)
+
+
+def g7_hetero():
+    for n in (20,):
+        pn = op.network.Cubic(shape=[n, n, n], spacing=1e-4)
+        g = 10.0 ** np.random.default_rng(0).uniform(-15, -12, pn.Nt)
+        linear_case(f"g7_cubic{n}_hetero", pn, g,
+                    value_bcs=[(pn.pores("left"), 2e5, "add"), (pn.pores("right"), 1e5, "add")],
+                    rate_pores={"left": pn.pores("left"), "right": pn.pores("right")})
+    # non-cubic aspect, rate + value BCs, some zero conductances
+    pn = op.network.Cubic(shape=[7, 5, 11])
+    rng = np.random.default_rng(1)
+    g = rng.uniform(0.5, 2.0, pn.Nt)
+    g[rng.choice(pn.Nt, 40, replace=False)] = 0.0
+    linear_case("g7_cubic_7x5x11_zero_g", pn, g,
+                value_bcs=[(pn.pores("back"), 3.0, "add")],
+                rate_bcs=[(pn.pores("front"), -0.25, "add")],
+                rate_pores={"front": pn.pores("front"), "back": pn.pores("back")})
+
+
+def g11_irregular():
+    # duplicate throats, a self-loop-free multigraph and zero conductances on a
+    # hand-made network (semantics of tocsr / eliminate_zeros / laplacian)
+    rng = np.random.default_rng(5)
+    Np = 40
+    coords = rng.random((Np, 3))
+    c = rng.integers(0, Np, size=(150, 2))
+    c = c[c[:, 0] != c[:, 1]]
+    c = np.sort(c, axis=1)
+    chain = np.vstack((np.arange(Np - 1), np.arange(1, Np))).T   # keep it connected
+    conns = np.vstack((c, chain, c[:10]))                        # 10 duplicated throats
+    pn = op.network.Network(coords=coords, conns=conns)
+    g = rng.uniform(1, 2, pn.Nt)
+    g[::17] = 0.0
+    linear_case("g11_multigraph_40", pn, g,
+                value_bcs=[(np.arange(0, 4), 1.5, "add"), (np.arange(36, 40), -0.5, "add")],
+                rate_pores={"in": np.arange(0, 4), "out": np.arange(36, 40)})
+    # Delaunay network, BC by coordinate (config 4 in miniature)
+    pts = np.random.default_rng(0).random((600, 3))
+    dn = op.network.Delaunay(points=pts, shape=[1, 1, 1], reflect=False)
+    co = oracle.delaunay_network(np.array(dn["pore.coords"]))
+    cr = np.array(dn["throat.conns"])
+    cr = cr[np.lexsort((cr[:, 1], cr[:, 0]))]
+    assert np.array_equal(co, cr), "oracle delaunay edges differ from reference"
+    x = dn["pore.coords"][:, 0]
+    g = 10.0 ** np.random.default_rng(2).uniform(-15, -12, dn.Nt)
+    linear_case("g12_delaunay_600", dn, g,
+                value_bcs=[(np.flatnonzero(x < 0.1), 1.0, "add"),
+                           (np.flatnonzero(x > 0.9), 0.0, "add")],
+                rate_pores={"in": np.flatnonzero(x < 0.1), "out": np.flatnonzero(x > 0.9)})
+    save("g12_delaunay_600_coords", coords=np.array(dn["pore.coords"]))
+
+
+def g8_big():
+    # config 1 scale: Cubic 50^3, SuperLU (~3 min)
+    n = 50
+    pn = op.network.Cubic(shape=[n, n, n], spacing=1e-4)
+    g = 10.0 ** np.random.default_rng(0).uniform(-15, -12, pn.Nt)
+    alg = linear_case("g8_cubic50_hetero", pn, g,
+                      value_bcs=[(pn.pores("left"), 2e5, "add"), (pn.pores("right"), 1e5, "add")],
+                      rate_pores={"left": pn.pores("left"), "right": pn.pores("right")},
+                      store_full=False)
+    del alg
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--big", action="store_true")
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    meta_path = os.path.join(HERE, "golden.json")
+    if os.path.exists(meta_path):
+        META.update(json.load(open(meta_path)))
+    cases = [g1_solvers, g2_stokes, g3_reactive, g4_csr, g5_conduit, g6_profiles,
+             g7_hetero, g11_irregular]
+    if args.big:
+        cases = [g8_big]
+    for fn in cases:
+        if args.only and args.only not in fn.__name__:
+            continue
+        fn()
+        op.Workspace().clear()
+    import scipy
+    META["_versions"] = dict(numpy=np.__version__, scipy=scipy.__version__,
+                             openpnm=str(op.__version__))
+    json.dump(META, open(meta_path, "w"), indent=1, sort_keys=True)
+    print("wrote", meta_path)

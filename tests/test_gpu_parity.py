@@ -1,0 +1,374 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the golden
+vectors of the real reference and against the CPU oracle on seeded inputs.
+
+Bars: CSR indptr/indices bit-exact; x and rate()
+within 1e-8 relative with CG rtol 1e-12; outer-iteration counts equal."""
+import numpy as np
+import pytest
+import scipy.sparse as sprs
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+X_RTOL = 1e-8          # north-star tolerance on pore values and rates
+
+LINEAR = ["g1_solvers_3x4x5", "g4_csr_4x3x2", "g6_two_values_9", "g6_value_rate_9",
+          "g7_cubic20_hetero", "g7_cubic_7x5x11_zero_g", "g11_multigraph_40",
+          "g12_delaunay_600"]
+
+
+def relerr(a, b):
+    scale = np.max(np.abs(b))
+    return np.max(np.abs(a - b)) / (scale if scale > 0 else 1.0)
+
+
+def make_alg(b2, g, cls=None):
+    Np = int(g["Np"]) if "Np" in g else g["x"].size
+    pn = b2.Network(conns=g["conns"], Np=Np)
+    ph = b2.Phase(pn)
+    ph["throat.conductance"] = g["g"]
+    alg = (cls or b2.Transport)(network=pn, phase=ph)
+    alg.settings._update({"quantity": "pore.x", "conductance": "throat.conductance"})
+    alg["pore.bc.value"] = g["bc_value"]
+    alg["pore.bc.rate"] = g["bc_rate"]
+    return pn, ph, alg
+
+
+@pytest.mark.parametrize("name", LINEAR)
+@pytest.mark.parametrize("fmt", ["auto", "csr"])
+def test_linear_golden(name, fmt, b2, golden, golden_meta):
+    g, m = golden(name), golden_meta[name]
+    pn, ph, alg = make_alg(b2, g)
+    solver = b2.B200PCG(tol=1e-13, fmt=fmt)
+    alg.run(solver=solver)
+    A = alg.A
+    assert np.array_equal(A.indptr, g["indptr"]), "indptr not bit-exact"
+    assert np.array_equal(A.indices, g["indices"]), "indices not bit-exact"
+    np.testing.assert_allclose(A.data, g["data"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(alg.b, g["b"], rtol=1e-12, atol=0)
+    assert A.nnz == m["nnz"]
+    assert alg.soln.is_converged and alg.soln.num_iter == m["num_iter"] == 1
+    assert relerr(alg.x, g["x"]) < X_RTOL
+    for lbl, val in m["rates"].items():
+        r = alg.rate(pores=g["pores_" + lbl])[0]
+        assert abs(r - val) <= X_RTOL * abs(val)
+        single = alg.rate(pores=g["pores_" + lbl], mode="single")
+        assert single.size == g["pores_" + lbl].size
+        assert np.isclose(single.sum(), r, rtol=1e-12)
+
+
+def test_pure_laplacian_matches_scipy(b2, golden):
+    g = golden("g11_multigraph_40")          # duplicated throats, zero conductances
+    Np = int(g["Np"])
+    ctx = b2.B200PCG().ctx
+    ctx.build_laplacian(g["conns"], g["g"], Np)
+    L = ctx.export_csr_scipy(0)
+    ref = oracle.to_csr(oracle.build_A(g["conns"], g["g"], Np), Np)
+    ref.sort_indices()
+    assert np.array_equal(L.indptr, ref.indptr) and np.array_equal(L.indices, ref.indices)
+    np.testing.assert_allclose(L.data, ref.data, rtol=1e-13, atol=0)
+    x = np.random.default_rng(0).random(Np)
+    y = ctx.spmv(0, x).cpu().numpy()
+    np.testing.assert_allclose(y, ref @ x, rtol=1e-12, atol=1e-12)
+
+
+def test_assembly_is_bitwise_repeatable(b2, golden):
+    g = golden("g12_delaunay_600")
+    Np = int(g["Np"])
+    outs = []
+    for _ in range(3):
+        ctx = b2.B200PCG().ctx
+        ctx.build_laplacian(g["conns"], g["g"], Np)
+        ctx.apply_bcs(g["bc_value"], g["bc_rate"])
+        ip, ix, dt = ctx.export_csr(1)
+        x, it, rel, info = ctx.pcg(rtol=1e-12)
+        outs.append((ip.cpu().numpy(), ix.cpu().numpy(), dt.cpu().numpy().view(np.uint64),
+                     x.cpu().numpy().view(np.uint64), it))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)          # no float atomics anywhere: bit-identical
+
+
+def test_b200pcg_solve_dropin_on_reference_style_coo(b2, golden, golden_meta):
+    """solver.solve(A=coo, b=b, x0=x0) exactly as _transport.py:213 calls it,
+    with A in the reference's own (unsorted, diagonal-last) COO layout."""
+    g = golden("g7_cubic20_hetero")
+    Np = int(g["Np"])
+    A, b, f = oracle.apply_bcs(oracle.build_A(g["conns"], g["g"], Np), Np, g["bc_value"],
+                               g["bc_rate"])
+    coo = sprs.coo_matrix((A[2], (A[0], A[1])), shape=(Np, Np))
+    x0 = np.zeros(Np)
+    solver = b2.B200PCG(tol=1e-13)
+    x, code = solver.solve(A=coo, b=b, x0=x0)
+    assert code == 0 and not x0.any()            # x0 must not be mutated
+    assert relerr(x, g["x"]) < X_RTOL
+    assert solver.info["fmt"] == "dia" and solver.info["ndiags"] == 3
+    # same system through the generic CSR operator
+    x2, code2 = b2.B200PCG(tol=1e-13, fmt="csr").solve(A=coo.tocsr(), b=b)
+    assert code2 == 0 and relerr(x2, g["x"]) < X_RTOL
+    # tolerance semantics of ScipyCG: ||b - A x|| <= tol ||b||
+    x3, code3 = b2.B200PCG(tol=1e-6).solve(A=coo, b=b)
+    M = coo.tocsr()
+    assert code3 == 0 and np.linalg.norm(M @ x3 - b) <= 1e-6 * np.linalg.norm(b) * (1 + 1e-6)
+    # maxiter reached -> truthy exit code, like scipy's info > 0
+    x4, code4 = b2.B200PCG(tol=1e-13, maxiter=3).solve(A=coo, b=b)
+    assert code4 > 0
+
+
+def test_solvers_test_known_answer(b2):
+    # tests/unit/algorithms/SolversTest.py:12-49 with the new solver
+    pn = b2.Cubic([3, 4, 5])
+    ph = b2.Phase(pn)
+    ph["throat.conductance"] = np.linspace(1, 5, pn.Nt)
+    alg = b2.Transport(network=pn, phase=ph)
+    alg.settings._update({"quantity": "pore.x", "conductance": "throat.conductance"})
+    alg.set_value_BC(pores=pn.pores("front"), values=1.0)
+    alg.set_value_BC(pores=pn.pores("bottom"), values=0.0, mode="overwrite")
+    alg.run(solver=b2.B200PCG())
+    np.testing.assert_allclose(alg.x.mean(), 0.624134, rtol=1e-5)
+    alg.run(solver=b2.B200PCG(tol=1e-13))
+    np.testing.assert_allclose(alg.x.mean(), 0.6241341116805926, rtol=1e-10)
+
+
+def test_subclassed_transport_known_answers(b2, golden):
+    # tests/unit/algorithms/SubclassedTransportTest.py:18-82
+    pn = b2.Cubic([9, 9, 9])
+    ph = b2.Phase(pn)
+    for k in ("hydraulic", "diffusive", "electrical", "thermal"):
+        ph[f"throat.{k}_conductance"] = 1.0
+    s = b2.B200PCG(tol=1e-13)
+    sf = b2.StokesFlow(network=pn, phase=ph)
+    sf.set_value_BC(pores=pn.pores("top"), values=101325)
+    sf.set_value_BC(pores=pn.pores("bottom"), values=0)
+    sf.run(solver=s)
+    rin, rout = sf.rate(pores=pn.pores("top"))[0], sf.rate(pores=pn.pores("bottom"))[0]
+    np.testing.assert_allclose(rin, 1025915.625, rtol=1e-9)
+    np.testing.assert_allclose(rin, -rout, rtol=1e-9)
+    assert relerr(sf["pore.pressure"], golden("g2_subclassed_9")["x_stokes"]) < X_RTOL
+    assert sf.soln.num_iter == 1
+    for cls, val in ((b2.FickianDiffusion, 10.125), (b2.OhmicConduction, 10.125)):
+        a = cls(network=pn, phase=ph)
+        a.set_value_BC(pores=pn.pores("top"), values=1)
+        a.set_value_BC(pores=pn.pores("bottom"), values=0)
+        a.run(solver=s)
+        np.testing.assert_allclose(a.rate(pores=pn.pores("top"))[0], val, rtol=1e-9)
+    fo = b2.FourierConduction(network=pn, phase=ph)
+    fo.set_value_BC(pores=pn.pores("top"), values=273)
+    fo.set_value_BC(pores=pn.pores("bottom"), values=0)
+    fo.run(solver=s)
+    np.testing.assert_allclose(fo.rate(pores=pn.pores("top"))[0], 2764.125, rtol=1e-9)
+
+
+def test_conduit_analytic(b2, golden_meta):
+    # tests/integration/Flow_in_straight_conduit.py:8-55
+    for row in golden_meta["g5_conduit"]:
+        pn = b2.Cubic([5, 1, 1])
+        ph = b2.Phase(pn)
+        ph["throat.hydraulic_conductance"] = np.array(row["g"])
+        sf = b2.StokesFlow(network=pn, phase=ph)
+        sf.set_value_BC(pores=pn.pores("xmin"), values=1.0)
+        sf.set_value_BC(pores=pn.pores("xmax"), values=0.0)
+        sf.run(solver=b2.B200PCG(tol=1e-14))
+        np.testing.assert_allclose(sf.rate(pores=pn.pores("xmin"))[0], row["Q"], rtol=1e-10)
+        np.testing.assert_allclose(sf.rate(throats=[0, 1, 2, 3], mode="single"),
+                                   row["Q"] * np.ones(4), rtol=1e-10)
+
+
+REACTIVE = ["g3_reactive_4_standard_kinetics", "g3_reactive_4_power_law", "g3_reactive_4_linear",
+            "g3_reactive_4_two_sources", "g9_reactive_10_power_law"]
+
+
+def reactive_alg(b2, g, m):
+    pn = b2.Network(conns=g["conns"], Np=g["x"].size)
+    ph = b2.Phase(pn)
+    ph["throat.diffusive_conductance"] = g["g"]
+    alg = b2.ReactiveTransport(network=pn, phase=ph)
+    alg.settings._update({"quantity": "pore.concentration",
+                          "conductance": "throat.diffusive_conductance"})
+    alg.settings._update(m["settings"])
+    for n, s in enumerate(m["sources"]):
+        kw = {}
+        for k, v in s["params"].items():
+            ph[f"pore.src{n}_{k}"] = v
+            kw[k] = f"pore.src{n}_{k}"
+        ph.add_model(propname=f"pore.reaction{n}", model=s["kind"], X="pore.concentration", **kw)
+        alg.set_source(pores=g[f"src{n}_pores"], propname=f"pore.reaction{n}")
+    bc = np.flatnonzero(np.isfinite(g["bc_value"]))
+    alg.set_value_BC(pores=bc, values=g["bc_value"][bc])
+    return pn, ph, alg
+
+
+@pytest.mark.parametrize("name", REACTIVE)
+def test_reactive_golden(name, b2, golden, golden_meta):
+    g, m = golden(name), golden_meta[name]
+    pn, ph, alg = reactive_alg(b2, g, m)
+    alg.run(solver=b2.B200PCG(tol=1e-13))
+    assert alg.soln.num_iter == m["num_iter"]            # same outer iterations
+    assert alg.soln.is_converged == m["is_converged"]
+    assert relerr(alg.x, g["x"]) < X_RTOL
+    np.testing.assert_allclose(alg.x.mean(), m["c_mean"], rtol=1e-8)
+    A = alg.A
+    assert np.array_equal(A.indptr, g["indptr"]) and np.array_equal(A.indices, g["indices"])
+    np.testing.assert_allclose(A.data, g["data"], rtol=1e-7, atol=0)
+    r = alg.rate(pores=g["src0_pores"])[0]
+    assert abs(r - m["rate_src0"]) <= 1e-7 * abs(m["rate_src0"])
+    # S1/S2/rate left on the phase (SourceTermTest.py:41-89: rate == S1*X + S2)
+    X = alg.x
+    S1, S2, rt = (ph[f"pore.reaction0.{k}"] for k in ("S1", "S2", "rate"))
+    np.testing.assert_allclose(rt, S1 * X + S2, rtol=1e-9, atol=1e-30)
+
+
+def test_reactive_divergence_is_reported(b2, golden, golden_meta):
+    # ReactiveTransportTest.py:162-174: relaxation_factor=20, newton_maxiter=25
+    name = "g3_reactive_4_diverge"
+    g, m = golden(name), golden_meta[name]
+    pn, ph, alg = reactive_alg(b2, g, m)
+    try:
+        alg.run(solver=b2.B200PCG(tol=1e-13))
+    except Exception as e:            # the reference may also raise on inf/nan
+        assert "inf/nan" in str(e)
+        return
+    assert not alg.soln.is_converged
+    assert alg.soln.num_iter == 25
+
+
+def test_validation_errors(b2):
+    # GenericTransportTest.py:63-89, 358-368
+    pn = b2.Cubic([4, 4, 4])
+    ph = b2.Phase(pn)
+    g = np.ones(pn.Nt)
+    g[5] = np.inf
+    ph["throat.g"] = g
+    alg = b2.Transport(network=pn, phase=ph, quantity="pore.x", conductance="throat.g")
+    alg.set_value_BC(pores=pn.pores("left"), values=1.0)
+    alg.set_value_BC(pores=pn.pores("right"), values=0.0)
+    with pytest.raises(Exception, match="inf/nan"):
+        alg.run()
+    ph["throat.g"] = np.ones(pn.Nt)
+    x0 = np.zeros(pn.Np)
+    x0[3] = np.nan
+    with pytest.raises(Exception, match="x0 contains inf/nan"):
+        alg.run(x0=x0)
+    alg.run(x0=np.full(pn.Np, 0.5))
+    assert alg.soln.is_converged
+    y = np.unique(np.around(alg.x, decimals=6))
+    np.testing.assert_allclose(y, [0, 1 / 3, 2 / 3, 1], atol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 2), (2, 1, 1), (17, 1, 1), (1, 33, 1), (5, 1, 7),
+                                   (3, 4, 5), (31, 2, 2)])
+def test_small_and_ragged_shapes_vs_oracle(shape, b2):
+    pn = b2.Cubic(shape)
+    rng = np.random.default_rng(sum(shape))
+    g = rng.uniform(0.1, 10.0, pn.Nt)
+    bcv = np.full(pn.Np, np.nan)
+    bcv[0] = 1.0
+    bcv[pn.Np - 1] = -2.0
+    ph = b2.Phase(pn)
+    ph["throat.g"] = g
+    alg = b2.Transport(network=pn, phase=ph, quantity="pore.x", conductance="throat.g")
+    alg["pore.bc.value"] = bcv
+    alg.run(solver=b2.B200PCG(tol=1e-14))
+    ref = oracle.transport_run(pn.conns, g, pn.Np, bc_value=bcv)
+    assert relerr(alg.x, ref["x"]) < X_RTOL
+    M = oracle.to_csr(ref["A"], pn.Np)
+    A = alg.A
+    assert np.array_equal(A.indptr, M.indptr) and np.array_equal(A.indices, M.indices)
+
+
+def test_self_loops_and_isolated_bc_pore(b2):
+    # self-loop throats are dropped by the Laplacian; an isolated pore with a BC is fine
+    conns = np.array([[0, 1], [1, 1], [1, 2], [2, 3], [0, 3], [2, 2]])
+    g = np.array([1.0, 5.0, 2.0, 3.0, 4.0, 7.0])
+    Np = 5
+    bcv = np.full(Np, np.nan)
+    bcv[0], bcv[4] = 1.0, 9.0
+    bcr = np.full(Np, np.nan)
+    bcr[2] = 0.5
+    ctx = b2.B200PCG().ctx
+    ctx.build_laplacian(conns, g, Np)
+    ctx.apply_bcs(bcv, bcr)
+    x, it, rel, info = ctx.pcg(rtol=1e-14)
+    pure = oracle.build_A(conns, g, Np)
+    A, b, f = oracle.apply_bcs(pure, Np, bcv, bcr)
+    M = oracle.to_csr(A, Np)
+    G = ctx.export_csr_scipy(1)
+    assert np.array_equal(G.indptr, M.indptr) and np.array_equal(G.indices, M.indices)
+    xr, _ = oracle.spsolve(M, b)
+    assert info == 0 and relerr(x.cpu().numpy(), xr) < X_RTOL
+
+
+def test_medium_cubic_cg_vs_cg(b2):
+    """Cubic 48^3, 3-decade heterogeneity: GPU PCG (both formats) against the
+    oracle's numpy Jacobi-PCG at rtol 1e-13, and iteration counts in family."""
+    n = 48
+    pn = b2.Cubic([n, n, n], spacing=1e-4, coords=False)
+    g = 10.0 ** np.random.default_rng(0).uniform(-15, -12, pn.Nt)
+    bcv = np.full(pn.Np, np.nan)
+    bcv[pn.pores("left")] = 2e5
+    bcv[pn.pores("right")] = 1e5
+    A, b, f = oracle.apply_bcs(oracle.build_A(pn.conns, g, pn.Np), pn.Np, bcv, None)
+    M = oracle.to_csr(A, pn.Np)
+    xr, info, its_ref = oracle.jacobi_pcg(M, b, rtol=1e-13)
+    assert info == 0
+    res = {}
+    for fmt in ("dia", "csr"):
+        ph = b2.Phase(pn)
+        ph["throat.hydraulic_conductance"] = g
+        sf = b2.StokesFlow(network=pn, phase=ph)
+        sf["pore.bc.value"] = bcv
+        sf.settings["validate_topology"] = False
+        s = b2.B200PCG(tol=1e-13, fmt=fmt)
+        sf.run(solver=s)
+        assert sf.soln.is_converged
+        assert relerr(sf.x, xr) < X_RTOL
+        assert s.ctx.pcg_format()[0] == {"dia": 2, "csr": 1}[fmt]
+        res[fmt] = sf.soln.cg_iters
+        rl = sf.rate(pores=pn.pores("left"))[0]
+        rr = sf.rate(pores=pn.pores("right"))[0]
+        assert abs(rl + rr) <= 1e-8 * abs(rl)               # conservation
+        rref = oracle.rate(pn.conns, g, xr, pores=pn.pores("left"))[0]
+        assert abs(rl - rref) <= X_RTOL * abs(rref)
+    for fmt, its in res.items():
+        assert 0.7 * its_ref <= its <= 1.3 * its_ref + 70, (fmt, its, its_ref)
+
+
+def test_large_properties_cubic_128(b2):
+    """Size-independent properties at a size the oracle does not solve:
+    residual, conservation, linearity and idempotence of the assembly."""
+    n = 128
+    pn = b2.Cubic([n, n, n], coords=False)
+    g = 10.0 ** np.random.default_rng(1).uniform(-15, -12, pn.Nt)
+    bcv = np.full(pn.Np, np.nan)
+    bcv[pn.pores("left")] = 1.0
+    bcv[pn.pores("right")] = 0.0
+    s = b2.B200PCG(tol=1e-10)
+    ctx = s.ctx
+    nnz_pure = ctx.build_laplacian(pn.conns, g, pn.Np)
+    assert nnz_pure == 2 * pn.Nt + pn.Np
+    f, nnz = ctx.apply_bcs(bcv, None)
+    # BC planes keep only their diagonal; their couplings vanish from both sides
+    nbc = 2 * n * n
+    t_bc = 2 * (2 * n * (n - 1)) + 2 * n * n          # throats touching a BC pore
+    assert nnz == nnz_pure - 2 * t_bc
+    x, it, rel, info = ctx.pcg(rtol=1e-10)
+    assert info == 0 and rel <= 1e-10 * (1 + 1e-6)
+    b = ctx.get_b()
+    r = ctx.spmv(1, x) - b
+    assert float(r.norm() / b.norm()) <= 1.01e-10           # independent residual check
+    rl = ctx.rate_pores(x, pn.pores("left")).sum().item()
+    rr = ctx.rate_pores(x, pn.pores("right")).sum().item()
+    assert abs(rl + rr) <= 1e-7 * abs(rl)
+    xn = x.cpu().numpy()
+    assert xn.min() >= -1e-9 and xn.max() <= 1 + 1e-9       # discrete maximum principle
+    # linearity: doubling the BC values doubles the solution
+    ctx.apply_bcs(2 * bcv, None)
+    x2, it2, rel2, info2 = ctx.pcg(rtol=1e-10)
+    assert info2 == 0 and float((x2 - 2 * x).abs().max()) < 1e-7
+    # idempotence: re-assembly gives bit-identical CSR
+    ip1, ix1, dt1 = (t.clone() for t in ctx.export_csr(1))
+    ctx.build_laplacian(pn.conns, g, pn.Np)
+    ctx.apply_bcs(2 * bcv, None)
+    ip2, ix2, dt2 = ctx.export_csr(1)
+    assert bool((ip1 == ip2).all()) and bool((ix1 == ix2).all()) and bool((dt1 == dt2).all())

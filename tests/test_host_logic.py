@@ -1,0 +1,99 @@
+"""CPU: host-side mirror of the reference interface (no compute)."""
+import numpy as np
+import pytest
+
+import openpnm_b200 as b2
+from oracle import oracle
+
+
+def test_cubic_matches_reference_numbering(golden):
+    g = golden("g7_cubic20_hetero")
+    pn = b2.Cubic([20, 20, 20], spacing=1e-4)
+    assert np.array_equal(pn["throat.conns"], g["conns"])
+    assert np.array_equal(pn.pores("left"), g["pores_left"])
+    assert np.array_equal(pn.pores("right"), g["pores_right"])
+    net = oracle.cubic_network([4, 3, 2])
+    pn = b2.Cubic([4, 3, 2])
+    for lbl in ("left", "right", "front", "back", "bottom", "top"):
+        assert np.array_equal(pn.pores(lbl), net["labels"][lbl])
+    assert pn.Nt == 46 and pn.Np == 24
+    np.testing.assert_allclose(pn["pore.coords"], net["coords"])
+
+
+def test_set_bc_bookkeeping():
+    # tests/unit/algorithms/BCTest.py:18-88
+    pn = b2.Cubic([3, 3, 3])
+    ph = b2.Phase(pn)
+    alg = b2.Transport(network=pn, phase=ph)
+    alg.set_value_BC(pores=[0, 1], values=1.0)
+    assert np.isfinite(alg["pore.bc.value"]).sum() == 2
+    with pytest.raises(Exception):
+        alg.set_rate_BC(pores=[1, 2], rates=1.0)            # 'add' over an existing BC
+    alg.set_rate_BC(pores=[1, 2], rates=3.0, mode="overwrite")
+    assert np.isnan(alg["pore.bc.value"][1]) and alg["pore.bc.rate"][1] == 3.0
+    alg.set_value_BC(pores=[5, 6], values=[1.0, 2.0])
+    assert alg["pore.bc.value"][6] == 2.0
+    with pytest.raises(Exception):
+        alg.set_value_BC(pores=[7, 8], values=[1.0, 2.0, 3.0])
+    alg.clear_rate_BCs()
+    assert np.isnan(alg["pore.bc.rate"]).all()
+    alg.set_BC(pores=None, bctype=[], mode="remove")
+    assert np.isnan(alg["pore.bc.value"]).all()
+    assert alg["pore.source"] == {}                         # GenericTransportTest.py:370-375
+    assert set(alg["pore.bc"].keys()) == {"rate", "value"}
+
+
+def test_source_bc_mutual_exclusion():
+    # tests/unit/algorithms/ReactiveTransportTest.py:79-95
+    pn = b2.Cubic([4, 4, 4])
+    ph = b2.Phase(pn)
+    ph.add_model(propname="pore.reaction", model="standard_kinetics", prefactor="pore.A",
+                 exponent="pore.k", X="pore.concentration")
+    alg = b2.ReactiveTransport(network=pn, phase=ph)
+    alg.settings._update({"quantity": "pore.concentration",
+                          "conductance": "throat.diffusive_conductance"})
+    alg.set_value_BC(pores=pn.pores("top"), values=1.0)
+    with pytest.raises(Exception):
+        alg.set_source(pores=pn.pores("top"), propname="pore.reaction")
+    alg.set_source(pores=pn.pores("bottom"), propname="pore.reaction")
+    with pytest.raises(Exception):
+        alg.set_value_BC(pores=pn.pores("bottom"), values=1.0)
+    assert alg["pore.source.reaction"].sum() == 16
+    alg.set_source(pores=pn.pores("bottom")[:4], propname="pore.reaction", mode="remove")
+    assert alg["pore.source.reaction"].sum() == 12
+    alg.set_source(pores=[], propname="pore.reaction", mode="clear")
+    assert alg["pore.source.reaction"].sum() == 0
+
+
+def test_settings_of_subclasses(golden_meta):
+    m = golden_meta["g2_subclassed_9"]
+    pn = b2.Cubic([2, 2, 2])
+    ph = b2.Phase(pn)
+    sf = b2.StokesFlow(network=pn, phase=ph)
+    fd = b2.FickianDiffusion(network=pn, phase=ph)
+    assert sf.settings["quantity"] == m["stokes_quantity"]
+    assert sf.settings["conductance"] == m["stokes_conductance"]
+    assert fd.settings["quantity"] == m["fickian_quantity"]
+    assert fd.settings["conductance"] == m["fickian_conductance"]
+    assert sf.settings.f_rtol == 1e-6 and sf.settings.newton_maxiter == 5000
+
+
+def test_clustered_topology_raises():
+    # tests/unit/algorithms/GenericTransportTest.py:51-61
+    pn = b2.Network(conns=[[0, 1], [1, 2], [3, 4]], Np=5)
+    ph = b2.Phase(pn)
+    ph["throat.g"] = 1.0
+    alg = b2.Transport(network=pn, phase=ph, quantity="pore.x", conductance="throat.g")
+    alg.set_value_BC(pores=[0], values=1.0)
+    alg.set_value_BC(pores=[2], values=0.0)
+    with pytest.raises(Exception, match="clustered"):
+        alg._validate_topology_health()
+    alg.set_value_BC(pores=[3], values=0.0)
+    alg._validate_topology_health()
+
+
+def test_solver_interface_shape():
+    s = b2.B200PCG()
+    assert s.tol == 1e-8 and hasattr(s, "maxiter") and callable(s.solve)
+    s = b2.B200PCG(tol=1e-10, maxiter=123)
+    assert s._get_atol(np.array([3.0, 4.0])) == pytest.approx(5e-10)

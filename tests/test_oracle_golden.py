@@ -1,0 +1,124 @@
+"""CPU: the oracle restatement against the golden vectors generated from the
+real reference (tests/golden/make_golden.py) and against the known-answer
+constants of the reference's own tests."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+LINEAR = ["g1_solvers_3x4x5", "g4_csr_4x3x2", "g6_two_values_9", "g6_value_rate_9",
+          "g7_cubic20_hetero", "g7_cubic_7x5x11_zero_g", "g11_multigraph_40",
+          "g12_delaunay_600"]
+
+
+@pytest.mark.parametrize("name", LINEAR)
+def test_linear_assembly_and_solution(name, golden, golden_meta):
+    g = golden(name)
+    Np = int(g["Np"])
+    pure = oracle.build_A(g["conns"], g["g"], Np)
+    A, b, f = oracle.apply_bcs(pure, Np, g["bc_value"], g["bc_rate"])
+    M = oracle.to_csr(A, Np)
+    assert np.array_equal(M.indptr, g["indptr"])          # bit-exact structure
+    assert np.array_equal(M.indices, g["indices"])
+    np.testing.assert_allclose(M.data, g["data"], rtol=1e-13, atol=0)
+    np.testing.assert_allclose(b, g["b"], rtol=1e-12, atol=0)
+    assert np.isclose(f, float(g["f"]), rtol=1e-14)
+    assert M.nnz == golden_meta[name]["nnz"]
+    x, code = oracle.spsolve(M, b)
+    assert code == 0
+    np.testing.assert_allclose(x, g["x"], rtol=1e-9, atol=0)
+    for lbl, val in golden_meta[name]["rates"].items():
+        r = oracle.rate(g["conns"], g["g"], x, pores=g["pores_" + lbl])[0]
+        assert np.isclose(r, val, rtol=1e-8)
+
+
+def test_known_answers_of_reference_tests(golden, golden_meta):
+    # tests/unit/algorithms/SolversTest.py:26-49
+    assert np.isclose(golden_meta["g1_solvers_3x4x5"]["x_mean"], 0.624134, rtol=1e-5)
+    assert np.isclose(golden_meta["g1_solvers_3x4x5"]["x_mean_scipycg"], 0.624134, rtol=1e-5)
+    # tests/unit/algorithms/SubclassedTransportTest.py:18-82
+    m = golden_meta["g2_subclassed_9"]
+    assert np.isclose(m["rate_in_stokes"], 1025915.625, rtol=1e-10)
+    assert np.isclose(m["rate_in_fickian"], 10.125, rtol=1e-10)
+    assert np.isclose(m["rate_in_stokes"], -m["rate_out_stokes"], rtol=1e-10)
+    # tests/unit/algorithms/ReactiveTransportTest.py:69-77, 97-112
+    assert np.isclose(golden_meta["g3_reactive_4_standard_kinetics"]["c_mean"], 0.717129, rtol=1e-6)
+    assert np.isclose(golden_meta["g3_reactive_4_two_sources"]["c_mean"], 0.666667, rtol=1e-6)
+    # tests/unit/algorithms/GenericTransportTest.py:114-135
+    y = np.unique(np.around(golden("g6_two_values_9")["x"], decimals=3))
+    assert np.allclose(y, np.linspace(0, 1, 9))
+    y = np.unique(np.around(golden("g6_value_rate_9")["x"], decimals=3))
+    assert np.allclose(y, np.arange(9.0))
+
+
+def test_stokes_9_oracle(golden, golden_meta):
+    net = oracle.cubic_network([9, 9, 9])
+    bcv = np.full(net["Np"], np.nan)
+    bcv[net["labels"]["top"]] = 101325
+    bcv[net["labels"]["bottom"]] = 0
+    out = oracle.transport_run(net["conns"], np.ones(net["Nt"]), net["Np"], bc_value=bcv)
+    np.testing.assert_allclose(out["x"], golden("g2_subclassed_9")["x_stokes"], rtol=1e-9, atol=1e-6)
+    r = oracle.rate(net["conns"], np.ones(net["Nt"]), out["x"], pores=net["labels"]["top"])[0]
+    assert np.isclose(r, 1025915.625, rtol=1e-9)
+    assert out["num_iter"] == golden_meta["g2_subclassed_9"]["num_iter"] == 1
+
+
+REACTIVE = ["g3_reactive_4_standard_kinetics", "g3_reactive_4_power_law", "g3_reactive_4_linear",
+            "g3_reactive_4_two_sources", "g9_reactive_10_power_law", "g3_reactive_4_diverge"]
+
+
+def reactive_sources(g, meta):
+    srcs = []
+    Np = g["x"].size
+    for n, s in enumerate(meta["sources"]):
+        mask = np.zeros(Np, dtype=bool)
+        mask[g[f"src{n}_pores"]] = True
+        srcs.append((mask, s["kind"], s["params"]))
+    return srcs
+
+
+@pytest.mark.parametrize("name", REACTIVE)
+def test_reactive_outer_loop(name, golden, golden_meta):
+    g, m = golden(name), golden_meta[name]
+    st = m["settings"]
+    out = oracle.picard_run(g["conns"], g["g"], g["x"].size, g["bc_value"], g["bc_rate"],
+                            reactive_sources(g, m), relaxation_factor=st["relaxation_factor"],
+                            newton_maxiter=st["newton_maxiter"], f_rtol=st["f_rtol"],
+                            x_rtol=st["x_rtol"])
+    assert out["num_iter"] == m["num_iter"]
+    assert out["is_converged"] == m["is_converged"]
+    if m["is_converged"]:
+        np.testing.assert_allclose(out["x"], g["x"], rtol=1e-9, atol=0)
+        assert np.isclose(out["x"].mean(), m["c_mean"], rtol=1e-10)
+        M = oracle.to_csr(out["A"], g["x"].size)
+        assert np.array_equal(M.indptr, g["indptr"]) and np.array_equal(M.indices, g["indices"])
+
+
+def test_cubic_generator_matches_reference_conns(golden):
+    g = golden("g7_cubic20_hetero")
+    net = oracle.cubic_network([20, 20, 20], spacing=1e-4)
+    assert np.array_equal(net["conns"], g["conns"])
+    assert np.array_equal(net["labels"]["left"], g["pores_left"])
+    assert np.array_equal(net["labels"]["right"], g["pores_right"])
+
+
+def test_conduit_analytic(golden_meta):
+    # tests/integration/Flow_in_straight_conduit.py:8-55
+    for row in golden_meta["g5_conduit"]:
+        g = np.array(row["g"])
+        conns = np.array([[0, 1], [1, 2], [2, 3], [3, 4]])
+        bcv = np.full(5, np.nan)
+        bcv[0], bcv[4] = 1.0, 0.0
+        out = oracle.transport_run(conns, g, 5, bc_value=bcv)
+        r = oracle.rate(conns, g, out["x"], pores=[0])[0]
+        assert np.isclose(r, row["Q"], rtol=1e-10)
+
+
+def test_jacobi_pcg_oracle_matches_direct(golden):
+    g = golden("g7_cubic20_hetero")
+    Np = int(g["Np"])
+    import scipy.sparse as sprs
+    M = sprs.csr_matrix((g["data"], g["indices"], g["indptr"]), shape=(Np, Np))
+    x, info, its = oracle.jacobi_pcg(M, g["b"], rtol=1e-13)
+    assert info == 0 and its > 10
+    np.testing.assert_allclose(x, g["x"], rtol=1e-8, atol=0)
