@@ -1,5 +1,7 @@
 // api.cu -- context lifecycle, statistics and the host-buffer entry points of
 // the C-ABI declared in include/b200pnm.h.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 extern "C" int b200_version(void) { return 100; }
@@ -12,6 +14,8 @@ extern "C" int b200_create(int device, b200_ctx** out) {
     return B200_ERR_CUDA;   // no CPU fallback: the product path needs the GPU
   b200_ctx* ctx = new b200_ctx();
   ctx->device = device;
+  const char* dbg = getenv("B200_DEBUG");
+  ctx->debug = dbg && dbg[0] && dbg[0] != '0';
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||

@@ -71,6 +71,7 @@ struct b200_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   std::string err;
+  bool debug = false;         // B200_DEBUG=1: trace the host loops on stderr
   int64_t launches = 0;
 
   // ownership (slab); single GPU: row_begin = 0, row_end = n_global

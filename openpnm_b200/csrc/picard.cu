@@ -103,6 +103,9 @@ extern "C" int b200_picard(b200_ctx* ctx, const double* x0, double relaxation,
     RET(b200_residual_norms(ctx, x, &r2, &x2));
     const double fn = sqrt(r2), xn = sqrt(x2), dxn = sqrt(dx2);
     if (f0 < 0.0) f0 = fn;
+    if (ctx->debug)
+      fprintf(stderr, "[b200 picard] i=%lld |R|=%.6e |R0|=%.6e |dx|=%.6e |x|=%.6e\n",
+              (long long)i, fn, f0, dxn, xn);
     // TerminationCondition.check: f_tol = inf, x_tol = inf
     if (fn == 0.0 || (fn / f_rtol <= f0 && dxn / x_rtol <= xn)) { conv = 1; break; }
     // _validate_linear_system (_transport.py:253-257)
@@ -147,17 +150,20 @@ __global__ void __launch_bounds__(256) k_rate_pores(const int* __restrict__ indp
   constexpr int G = 8;
   const int lane = threadIdx.x % G;
   const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) / G;
-  for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; q < k; q += gstride) {
-    const int64_t r = pores[q] - rb;
+  const int64_t kround = (k + (32 / G) - 1) / (32 / G) * (32 / G);   // warp-uniform trips
+  for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; q < kround; q += gstride) {
     double s = 0.0;
-    if (r < 0 || r >= n) {
-      if (lane == 0) flags[FLAG_INDEX] = 1;
-    } else {
-      for (int e = indptr[r] + lane; e < indptr[r + 1]; e += G) s += data[e] * x[indices[e]];
+    if (q < k) {
+      const int64_t r = pores[q] - rb;
+      if (r < 0 || r >= n) {
+        if (lane == 0) flags[FLAG_INDEX] = 1;
+      } else {
+        for (int e = indptr[r] + lane; e < indptr[r + 1]; e += G) s += data[e] * x[indices[e]];
+      }
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
-    if (lane == 0) out[q] = s;
+    if (lane == 0 && q < k) out[q] = s;
   }
 }
 

@@ -54,13 +54,18 @@ __global__ void __launch_bounds__(256) k_spmv_csr_vec(const int* __restrict__ in
                                                       double* __restrict__ y) {
   const int lane = threadIdx.x % G;
   const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) / G;
-  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; r < n; r += gstride) {
+  // the trip count is warp-uniform (rows rounded up to a whole warp of groups):
+  // every lane reaches the full-mask shuffles, idle groups just add zeros
+  const int64_t nround = (n + (32 / G) - 1) / (32 / G) * (32 / G);
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; r < nround; r += gstride) {
     double s = 0.0;
-    const int e1 = indptr[r + 1];
-    for (int e = indptr[r] + lane; e < e1; e += G) s += data[e] * x[indices[e] - col_shift];
+    if (r < n) {
+      const int e1 = indptr[r + 1];
+      for (int e = indptr[r] + lane; e < e1; e += G) s += data[e] * x[indices[e] - col_shift];
+    }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
-    if (lane == 0) y[r] = s;
+    if (lane == 0 && r < n) y[r] = s;
   }
 }
 
@@ -163,13 +168,16 @@ __global__ void __launch_bounds__(256) k_residual_norms(const int* __restrict__ 
   const int lane = threadIdx.x % G;
   const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) / G;
   double r2 = 0.0, x2 = 0.0;
-  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; r < n; r += gstride) {
+  const int64_t nround = (n + (32 / G) - 1) / (32 / G) * (32 / G);   // warp-uniform trips
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; r < nround; r += gstride) {
     double s = 0.0;
-    const int e1 = indptr[r + 1];
-    for (int e = indptr[r] + lane; e < e1; e += G) s += data[e] * x[indices[e]];
+    if (r < n) {
+      const int e1 = indptr[r + 1];
+      for (int e = indptr[r] + lane; e < e1; e += G) s += data[e] * x[indices[e]];
+    }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
-    if (lane == 0) {
+    if (lane == 0 && r < n) {
       const double res = s - b[r];
       r2 += res * res;
       x2 += x[r] * x[r];
@@ -864,6 +872,9 @@ extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double ato
     true2 = ctx->scal_h[cur + 1];
     const double pap = ctx->scal_h[SC_PAP];
     const double rrn = ctx->scal_h[cur];
+    if (ctx->debug)
+      fprintf(stderr, "[b200 pcg] it=%lld batch=%d true2=%.3e tol2=%.3e rr=%.3e pAp=%.3e\n",
+              (long long)it, batch, true2, tol2, rrn, pap);
     if (!isfinite(true2) || !isfinite(pap) || !isfinite(rrn)) { inf = -1; break; }
     if (rrn > 0.0 && !(pap > 0.0)) { inf = -1; break; }   // not SPD: breakdown
     if (true2 <= tol2) {
@@ -878,6 +889,9 @@ extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double ato
                          ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
       true2 = ctx->scal_h[cur + 1];
+      if (ctx->debug)
+        fprintf(stderr, "[b200 pcg] verify it=%lld true2=%.3e tol2=%.3e restarts=%d\n",
+                (long long)it, true2, tol2, restarts);
       if (true2 <= tol2 * (1.0 + 1e-6) || restarts >= 4) { done = true; break; }
       ++restarts;
       prev_true2 = true2;
