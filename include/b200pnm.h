@@ -171,6 +171,13 @@ typedef struct b200_stats {
 } b200_stats;
 int b200_get_stats(b200_ctx* ctx, b200_stats* out);
 
+/* Measurement hook for bench.py: average CUDA-event time of `reps` back-to-back
+ * launches of one kernel of the prepared PCG on its resident data (call after
+ * a solve; it scribbles on the PCG work vectors).  which: 0 = K_A SpMV + dot
+ * on the scaled operator, 1 = K_B x/r update + norms, 2 = K_C p update,
+ * 3 = K3 plain CSR SpMV of the system matrix.                                */
+int b200_time_kernel(b200_ctx* ctx, int which, int reps, double* ms_avg);
+
 /* --------------------------------------------------- host-buffer entry points
  * What a ctypes binder holding numpy arrays calls; H2D/D2H copies inside.
  * b200_solve_coo_h is the whole of `B200PCG.solve(A, b, x0)`.               */

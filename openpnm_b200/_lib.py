@@ -71,6 +71,7 @@ SIGNATURES = {
     "b200_rate_pores": (C.c_int, [_p, _p, _p, _i64, _p]),
     "b200_rate_throats": (C.c_int, [_p, _p, _p, _p, _p, _i64, _p]),
     "b200_get_stats": (C.c_int, [_p, C.POINTER(Stats)]),
+    "b200_time_kernel": (C.c_int, [_p, C.c_int, C.c_int, _pdbl]),
     "b200_solve_coo_h": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _dbl, _dbl, _i64, _p,
                                    _pi64, _pdbl, _pint]),
     "b200_nccl_unique_id": (C.c_int, [_p]),

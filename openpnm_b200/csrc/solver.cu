@@ -539,12 +539,14 @@ __global__ void __launch_bounds__(PCG_T) k_dia_spmv_dot(DiaPack A, const double*
 template <bool UNIT>
 __global__ void __launch_bounds__(PCG_T) k_csr_stream_spmv_dot(
     const int* __restrict__ optr, const int* __restrict__ ocols, const double* __restrict__ ovals,
-    const int* __restrict__ rowstart, const double* __restrict__ p, const double* __restrict__ dexp,
-    double* __restrict__ ap, double* part, unsigned* ticket, double* out_pap) {
+    const int* __restrict__ rowstart, int nblocks, const double* __restrict__ p,
+    const double* __restrict__ dexp, double* __restrict__ ap, double* part, unsigned* ticket,
+    double* out_pap) {
   extern __shared__ double prod[];
   double dot = 0.0;
-  const int r0 = rowstart[blockIdx.x], r1 = rowstart[blockIdx.x + 1];
-  if (r1 > r0) {
+  // persistent CTAs: row blocks are dealt round-robin
+  for (int q = blockIdx.x; q < nblocks; q += gridDim.x) {
+    const int r0 = rowstart[q], r1 = rowstart[q + 1];
     const int e0 = optr[r0], e1 = optr[r1];
     for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) prod[e - e0] = ovals[e] * p[ocols[e]];
     __syncthreads();
@@ -556,6 +558,7 @@ __global__ void __launch_bounds__(PCG_T) k_csr_stream_spmv_dot(
       ap[r] = acc;
       dot += pi * acc;
     }
+    __syncthreads();
   }
   double v[1] = {dot};
   double* o[1] = {out_pap};
@@ -748,14 +751,16 @@ static int launch_spmv_dot(b200_ctx* ctx, const double* p_owned, double* ap_owne
 #undef DIA_CASE
   } else if (ctx->o_maxrow <= CSR_MAXROW) {
     const size_t smem = (size_t)(CSR_Q + ctx->o_maxrow + 1) * sizeof(double);
+    const int nb = (int)ctx->o_nblocks;
+    const int g = nb < 148 * 8 ? nb : 148 * 8;
     if (ctx->unit_diag)
-      LAUNCH(ctx, k_csr_stream_spmv_dot<true>, (int)ctx->o_nblocks, PCG_T, smem,
-             ctx->o_indptr.as<int>(), ctx->o_cols.as<int>(), ctx->o_vals.as<double>(),
-             ctx->o_rowstart.as<int>(), p_owned, dexp, ap_owned, part, ticket, out);
+      LAUNCH(ctx, k_csr_stream_spmv_dot<true>, g, PCG_T, smem, ctx->o_indptr.as<int>(),
+             ctx->o_cols.as<int>(), ctx->o_vals.as<double>(), ctx->o_rowstart.as<int>(), nb,
+             p_owned, dexp, ap_owned, part, ticket, out);
     else
-      LAUNCH(ctx, k_csr_stream_spmv_dot<false>, (int)ctx->o_nblocks, PCG_T, smem,
-             ctx->o_indptr.as<int>(), ctx->o_cols.as<int>(), ctx->o_vals.as<double>(),
-             ctx->o_rowstart.as<int>(), p_owned, dexp, ap_owned, part, ticket, out);
+      LAUNCH(ctx, k_csr_stream_spmv_dot<false>, g, PCG_T, smem, ctx->o_indptr.as<int>(),
+             ctx->o_cols.as<int>(), ctx->o_vals.as<double>(), ctx->o_rowstart.as<int>(), nb,
+             p_owned, dexp, ap_owned, part, ticket, out);
   } else {
     const int g = grid_for(n * 32, PCG_T);
     if (ctx->unit_diag)
@@ -929,5 +934,44 @@ extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double ato
   if (iters) *iters = it;
   if (relres) *relres = rel;
   if (info) *info = inf;
+  return B200_OK;
+}
+
+extern "C" int b200_time_kernel(b200_ctx* ctx, int which, int reps, double* ms_avg) {
+  if (!ctx || !ctx->have_sys || reps < 1 || !ms_avg) return B200_ERR_ARG;
+  if (ctx->fmt == B200_FMT_NONE) FAIL(B200_ERR_ARG, "time_kernel: run a solve first");
+  CK(cudaSetDevice(ctx->device));
+  const int64_t n = ctx->n, pad = ctx->pad;
+  double* sc = ctx->scal.as<double>();
+  double* part = ctx->w_part.as<double>();
+  unsigned* ticket = ctx->w_ticket.as<unsigned>();
+  double* xt = owned(ctx->vx, pad);
+  double* r = owned(ctx->vr, pad);
+  double* p = owned(ctx->vp, pad);
+  double* ap = owned(ctx->vap, pad);
+  const double* d = cur_diag(ctx);
+  const int g2 = pcg_grid(ctx, 2);
+  // warm-up launch, then the timed train
+  for (int rep = -1; rep < reps; ++rep) {
+    if (rep == 0) CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    switch (which) {
+      case 0: RET(launch_spmv_dot(ctx, p, ap, sc + SC_AUX2)); break;
+      case 1:
+        LAUNCH(ctx, k_update_xr<true>, g2, PCG_T, 0, xt, r, p, ap, d, n, sc, SC_AUX0, SC_AUX1,
+               part, ticket, sc);
+        break;
+      case 2: LAUNCH(ctx, k_update_p, g2, PCG_T, 0, p, r, n, sc, SC_AUX0, SC_AUX1); break;
+      case 3:
+        RET(b200_spmv_csr_raw(ctx, ctx->sys_indptr.as<int>(), ctx->sys_indices.as<int>(),
+                              ctx->sys_data.as<double>(), n, ctx->row_begin, p - 0, ap));
+        break;
+      default: FAIL(B200_ERR_ARG, "time_kernel: which must be 0..3");
+    }
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *ms_avg = (double)ms / reps;
   return B200_OK;
 }

@@ -254,6 +254,11 @@ class Context:
                                             self._p(throats), int(throats.numel()), self._p(out)))
         return out
 
+    def time_kernel(self, which, reps=20):
+        ms = C.c_double()
+        self._ck(self.lib.b200_time_kernel(self._h, int(which), int(reps), C.byref(ms)))
+        return ms.value
+
     def stats(self):
         s = _lib.Stats()
         self._ck(self.lib.b200_get_stats(self._h, C.byref(s)))
@@ -275,3 +280,19 @@ class Context:
             C.byref(info)))
         self.n = int(n)
         return x, it.value, rel.value, info.value
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked host memory (for async H2D/D2H)."""
+    torch = _torch()
+    tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.int64): torch.int64,
+           np.dtype(np.int32): torch.int32, np.dtype(np.uint8): torch.uint8}[np.dtype(dtype)]
+    t = torch.empty(tuple(np.atleast_1d(shape).tolist()), dtype=tdt, pin_memory=True)
+    return t.numpy()
+
+
+def pinned_copy(a):
+    a = np.asarray(a)
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out

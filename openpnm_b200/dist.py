@@ -1,0 +1,216 @@
+"""Slab (row-block) partition of a network over the GPUs of one box.
+
+One process per GPU.  torch.distributed is the plumbing (rendezvous, the
+broadcast of the NCCL unique id, the gather of the result); the per-iteration
+halo exchange and dot-product all-reduce happen inside libb200pnm.so on its own
+NCCL communicator, enqueued on the same stream as the kernels.
+
+Partitioning: contiguous pore-index ranges.  For
+`Cubic` the index is x-major (openpnm/_skgraph/generators/_cubic.py:33-36), so
+rank r owns whole y-z planes and its halo is one plane per side.  Any network
+whose pores are numbered so that throats only join nearby indices (e.g. a
+Delaunay network sorted by x) works the same way: the halo is the contiguous
+window of `bandwidth` indices on either side.
+
+The reference's statement of this algorithm is its PETSc wrapper
+(openpnm/solvers/_petsc.py:117-128 row-block ownership, :160 cg + jacobi).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["slab_ranges", "cubic_slab_ranges", "slab_throat_mask", "cubic_slab_throats",
+           "bandwidth", "coordinate_order", "SlabSolver", "init_process_group"]
+
+
+# ------------------------------------------------------------ host-side plan
+def slab_ranges(Np, nranks, align=1):
+    """Balanced contiguous row ranges [(begin, end)] with ends on multiples of
+    `align` (a plane size) whenever that leaves every rank non-empty."""
+    units = Np // align
+    if Np % align or units < nranks:
+        align, units = 1, Np
+    base, extra = divmod(units, nranks)
+    out, b = [], 0
+    for r in range(nranks):
+        e = b + (base + (1 if r < extra else 0)) * align
+        out.append((b, e))
+        b = e
+    assert b == Np
+    return out
+
+
+def cubic_slab_ranges(shape, nranks):
+    nx, ny, nz = (int(s) for s in shape)
+    return slab_ranges(nx * ny * nz, nranks, align=ny * nz)
+
+
+def slab_throat_mask(conns, row_begin, row_end):
+    """Throats with at least one end in [row_begin, row_end): exactly the
+    throats that contribute to the rows a rank owns."""
+    c = np.asarray(conns)
+    a = (c[:, 0] >= row_begin) & (c[:, 0] < row_end)
+    b = (c[:, 1] >= row_begin) & (c[:, 1] < row_end)
+    return a | b
+
+
+def cubic_slab_throats(shape, x0, x1):
+    """Global throat ids and conns of a Cubic network restricted to the throats
+    touching the planes x0 <= x < x1, without building the full network.
+    Throat numbering follows the reference generator: all z-neighbour pairs,
+    then all y-, then all x- (openpnm/_skgraph/generators/_cubic.py:40-42,69-73),
+    each block in pore-index order."""
+    nx, ny, nz = (int(s) for s in shape)
+    ids, tails, heads = [], [], []
+    xs = np.arange(x0, x1, dtype=np.int64)
+    # z-throats: pore (x,y,z) -- (x,y,z+1), id = x*ny*(nz-1) + y*(nz-1) + z
+    if nz > 1:
+        X, Y, Z = np.meshgrid(xs, np.arange(ny, dtype=np.int64), np.arange(nz - 1, dtype=np.int64),
+                              indexing="ij")
+        t = (X * ny + Y) * nz + Z
+        ids.append(((X * ny + Y) * (nz - 1) + Z).ravel())
+        tails.append(t.ravel())
+        heads.append(t.ravel() + 1)
+    off = nx * ny * (nz - 1)
+    # y-throats: (x,y,z) -- (x,y+1,z), id = off + x*(ny-1)*nz + y*nz + z
+    if ny > 1:
+        X, Y, Z = np.meshgrid(xs, np.arange(ny - 1, dtype=np.int64), np.arange(nz, dtype=np.int64),
+                              indexing="ij")
+        t = (X * ny + Y) * nz + Z
+        ids.append((off + (X * (ny - 1) + Y) * nz + Z).ravel())
+        tails.append(t.ravel())
+        heads.append(t.ravel() + nz)
+    off += nx * (ny - 1) * nz
+    # x-throats: (x,y,z) -- (x+1,y,z) for x0-1 <= x < x1 (both cut planes included)
+    if nx > 1:
+        xa = np.arange(max(x0 - 1, 0), min(x1, nx - 1), dtype=np.int64)
+        X, Y, Z = np.meshgrid(xa, np.arange(ny, dtype=np.int64), np.arange(nz, dtype=np.int64),
+                              indexing="ij")
+        t = (X * ny + Y) * nz + Z
+        ids.append((off + t).ravel())
+        tails.append(t.ravel())
+        heads.append(t.ravel() + ny * nz)
+    ids = np.concatenate(ids) if ids else np.zeros(0, dtype=np.int64)
+    conns = np.empty((ids.size, 2), dtype=np.int64)
+    if ids.size:
+        conns[:, 0] = np.concatenate(tails)
+        conns[:, 1] = np.concatenate(heads)
+    return ids, conns
+
+
+def bandwidth(conns):
+    """max |c1 - c0|: the halo width a slab partition of this numbering needs."""
+    c = np.asarray(conns)
+    return int(np.abs(c[:, 1] - c[:, 0]).max()) if c.size else 0
+
+
+def coordinate_order(coords, axis=0):
+    """Permutation that renumbers pores by a coordinate (north star: "pore
+    ordering by coordinate").  Returns (perm, inverse): new index k holds old
+    pore perm[k]; inverse[old] = new."""
+    perm = np.argsort(np.asarray(coords)[:, axis], kind="stable")
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    return perm, inv
+
+
+# --------------------------------------------------------------- processes
+def init_process_group(backend=None):
+    """Join the torch.distributed job described by RANK / WORLD_SIZE /
+    MASTER_ADDR / MASTER_PORT (torchrun).  Returns (rank, world, local_rank)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local
+
+
+class SlabSolver:
+    """Per-rank driver: owns a device Context for rows [row_begin, row_end).
+
+    Usage on every rank:
+        ss = SlabSolver(Np, row_begin, row_end, device=local_rank)
+        ss.assemble(conns_local, g_local, bc_value, bc_rate)   # global-length bc arrays
+        x_local, iters, relres, info = ss.solve(rtol)
+    """
+
+    def __init__(self, Np, row_begin, row_end, device=0, fmt="auto"):
+        import torch
+        import torch.distributed as dist
+        from .device import Context
+        from . import _lib
+        self.Np, self.row_begin, self.row_end = int(Np), int(row_begin), int(row_end)
+        self.ctx = Context(device)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.ctx.set_format({"auto": 0, "csr": _lib.FMT_CSR, "dia": _lib.FMT_DIA}[fmt])
+        if self.world > 1:
+            buf = (C.c_ubyte * 128)()
+            if self.rank == 0:
+                rc = self.ctx.lib.b200_nccl_unique_id(C.cast(buf, C.c_void_p))
+                if rc != 0:
+                    raise RuntimeError("b200_nccl_unique_id failed")
+            t = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
+            if dist.get_backend() == "nccl":
+                t = t.cuda(device)
+            dist.broadcast(t, src=0)
+            raw = bytes(t.cpu().tolist())
+            idbuf = (C.c_ubyte * 128).from_buffer_copy(raw)
+            self.ctx._ck(self.ctx.lib.b200_comm_init(self.ctx._h, self.world, self.rank,
+                                                     C.cast(idbuf, C.c_void_p)))
+
+    def assemble(self, conns_local, g_local, bc_value=None, bc_rate=None):
+        import torch
+        import torch.distributed as dist
+        ctx = self.ctx
+        nnz = ctx.build_laplacian(conns_local, g_local, self.Np, self.row_begin, self.row_end)
+        if self.world > 1:
+            s, c = ctx.pure_diag_sum()
+            t = torch.tensor([s, float(c)], dtype=torch.float64)
+            if dist.get_backend() == "nccl":
+                t = t.cuda(ctx.device)
+            dist.all_reduce(t)          # f = global mean of the pure diagonal
+            t = t.cpu()
+            ctx.set_diag_mean(float(t[0] / t[1]))
+        f, nnz_sys = ctx.apply_bcs(bc_value, bc_rate)
+        return f, nnz, nnz_sys
+
+    def solve(self, rtol=1e-10, maxiter=0, x0=None):
+        return self.ctx.pcg(x0=x0, rtol=rtol, maxiter=maxiter)
+
+    def rate(self, x_global_dev, pores):
+        """Sum of the net rates of the pores this rank owns (caller all-reduces)."""
+        pores = np.asarray(pores, dtype=np.int64)
+        mine = pores[(pores >= self.row_begin) & (pores < self.row_end)]
+        if mine.size == 0:
+            return 0.0
+        return float(self.ctx.rate_pores(x_global_dev, mine).sum().item())
+
+    def gather(self, x_local):
+        """All ranks receive the full solution (like PETSc's Scatter().toAll,
+        openpnm/solvers/_petsc.py:225)."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return x_local
+        n = torch.tensor([x_local.numel()], dtype=torch.int64, device=x_local.device)
+        sizes = [torch.zeros_like(n) for _ in range(self.world)]
+        self.ctx.synchronize()
+        dist.all_gather(sizes, n)
+        sizes = [int(s.item()) for s in sizes]
+        m = max(sizes)
+        mine = torch.zeros(m, dtype=x_local.dtype, device=x_local.device)
+        mine[:x_local.numel()] = x_local
+        parts = [torch.empty(m, dtype=x_local.dtype, device=x_local.device) for _ in sizes]
+        dist.all_gather(parts, mine)
+        return torch.cat([p[:k] for p, k in zip(parts, sizes)])
