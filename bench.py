@@ -281,7 +281,7 @@ def gpu_arm(args):
         fmt_spmv = (nd + 2) * 8 * n_loc
     else:
         fmt_spmv = 12 * (nnz_loc - n_loc) + 4 * n_loc + 16 * n_loc
-    fmt_iter = fmt_spmv + 48 * n_loc + 24 * n_loc
+    fmt_iter = fmt_spmv + 24 * n_loc + 40 * n_loc
     peak, peak_src = peaks()
     ms_iter = float(np.mean(t_solve_ms)) / max(cg_iters, 1)
 

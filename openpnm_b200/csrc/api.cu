@@ -25,6 +25,8 @@ extern "C" int b200_create(int device, b200_ctx** out) {
     delete ctx;
     return B200_ERR_CUDA;
   }
+  cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+  if (ctx->num_sms < 1) ctx->num_sms = 148;
   *out = ctx;
   return B200_OK;
 }

@@ -68,6 +68,7 @@ enum {
 
 struct b200_ctx {
   int device = 0;
+  int num_sms = 148;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   std::string err;

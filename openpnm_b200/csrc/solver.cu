@@ -590,38 +590,35 @@ __global__ void __launch_bounds__(PCG_T) k_csr_warp_spmv_dot(
   grid_sum_finalize<1>(v, part, ticket, o);
 }
 
-// ---- K_B: x += alpha p ; r -= alpha Ap ; rr' = r.r  (and sum d r^2 when asked)
+// ---- K_B: r -= alpha Ap ; rr' = r.r  (and sum d r^2 when asked).  The x update
+// lives in K_C, where p is read anyway: 24 B/row here instead of 48.
 template <bool TRUE_NORM>
-__global__ void __launch_bounds__(PCG_T) k_update_xr(double* __restrict__ x, double* __restrict__ r,
-                                                     const double* __restrict__ p,
-                                                     const double* __restrict__ ap,
-                                                     const double* __restrict__ diag, int64_t n,
-                                                     const double* __restrict__ sc, int rr_in,
-                                                     int rr_out, double* part, unsigned* ticket,
-                                                     double* scw) {
+__global__ void __launch_bounds__(PCG_T) k_update_r(double* __restrict__ r,
+                                                    const double* __restrict__ ap,
+                                                    const double* __restrict__ diag, int64_t n,
+                                                    const double* __restrict__ sc, int rr_in,
+                                                    int rr_out, double* part, unsigned* ticket,
+                                                    double* scw) {
   const double rr = sc[rr_in], pap = sc[SC_PAP];
   const double alpha = (pap > 0.0 || pap < 0.0) ? rr / pap : 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   double s = 0.0, t = 0.0;
   const int64_t n2 = n >> 1;
-  double2* x2 = reinterpret_cast<double2*>(x);
   double2* r2 = reinterpret_cast<double2*>(r);
-  const double2* p2 = reinterpret_cast<const double2*>(p);
   const double2* a2 = reinterpret_cast<const double2*>(ap);
   const double2* d2 = reinterpret_cast<const double2*>(diag);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
-    double2 xv = x2[i], rv = r2[i];
-    const double2 pv = p2[i], av = a2[i];
-    xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+    double2 rv = r2[i];
+    const double2 av = a2[i];
     rv.x -= alpha * av.x; rv.y -= alpha * av.y;
-    x2[i] = xv; r2[i] = rv;
+    r2[i] = rv;
     s += rv.x * rv.x + rv.y * rv.y;
     if (TRUE_NORM) { const double2 dv = d2[i]; t += dv.x * rv.x * rv.x + dv.y * rv.y * rv.y; }
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const int64_t i = n - 1;
-    const double xn = x[i] + alpha * p[i], rn = r[i] - alpha * ap[i];
-    x[i] = xn; r[i] = rn;
+    const double rn = r[i] - alpha * ap[i];
+    r[i] = rn;
     s += rn * rn;
     if (TRUE_NORM) t += diag[i] * rn * rn;
   }
@@ -636,24 +633,34 @@ __global__ void __launch_bounds__(PCG_T) k_update_xr(double* __restrict__ x, dou
   }
 }
 
-// ---- K_C: p = r + beta p
-__global__ void __launch_bounds__(PCG_T) k_update_p(double* __restrict__ p,
-                                                    const double* __restrict__ r, int64_t n,
-                                                    const double* __restrict__ sc, int rr_old,
-                                                    int rr_new) {
-  const double ro = sc[rr_old], rn = sc[rr_new];
+// ---- K_C: x += alpha p ; p = r + beta p   (alpha, beta from the device scalars)
+__global__ void __launch_bounds__(PCG_T) k_update_xp(double* __restrict__ x,
+                                                     double* __restrict__ p,
+                                                     const double* __restrict__ r, int64_t n,
+                                                     const double* __restrict__ sc, int rr_old,
+                                                     int rr_new) {
+  const double ro = sc[rr_old], rn = sc[rr_new], pap = sc[SC_PAP];
+  const double alpha = (pap > 0.0 || pap < 0.0) ? ro / pap : 0.0;
   const double beta = (ro > 0.0) ? rn / ro : 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n2 = n >> 1;
+  double2* x2 = reinterpret_cast<double2*>(x);
   double2* p2 = reinterpret_cast<double2*>(p);
   const double2* r2 = reinterpret_cast<const double2*>(r);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
-    double2 pv = p2[i];
+    double2 pv = p2[i], xv = x2[i];
     const double2 rv = r2[i];
+    xv.x += alpha * pv.x; xv.y += alpha * pv.y;
     pv.x = rv.x + beta * pv.x; pv.y = rv.y + beta * pv.y;
+    x2[i] = xv;
     p2[i] = pv;
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = r[n - 1] + beta * p[n - 1];
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t i = n - 1;
+    const double po = p[i];
+    x[i] += alpha * po;
+    p[i] = r[i] + beta * po;
+  }
 }
 
 // ---- setup / teardown kernels
@@ -737,12 +744,21 @@ static int launch_spmv_dot(b200_ctx* ctx, const double* p_owned, double* ap_owne
   const double* dexp = ctx->dexp.as<double>();
   const int64_t n = ctx->n;
   if (ctx->fmt == B200_FMT_DIA) {
-    const int g = pcg_grid(ctx, 1);
+    // one full wave: resident CTAs per SM (from the occupancy calculator, the
+    // register count differs per ND) x SM count, grid-stride inside
 #define DIA_CASE(ND)                                                                       \
-  case ND:                                                                                 \
-    LAUNCH(ctx, (k_dia_spmv_dot<ND, true>), g, PCG_T, 0, ctx->dia, p_owned, dexp, ap_owned, n, \
-           part, ticket, out);                                                             \
-    break;
+  case ND: {                                                                               \
+    static int occ = 0;                                                                    \
+    if (!occ) {                                                                            \
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dia_spmv_dot<ND, true>,     \
+                                                       PCG_T, 0));                         \
+      if (occ < 1) occ = 1;                                                                \
+    }                                                                                      \
+    int64_t g = (n + PCG_T - 1) / PCG_T;                                                   \
+    if (g > (int64_t)occ * ctx->num_sms) g = (int64_t)occ * ctx->num_sms;                  \
+    LAUNCH(ctx, (k_dia_spmv_dot<ND, true>), (int)g, PCG_T, 0, ctx->dia, p_owned, dexp,     \
+           ap_owned, n, part, ticket, out);                                                \
+  } break;
     switch (ctx->dia.nd) {
       DIA_CASE(1) DIA_CASE(2) DIA_CASE(3) DIA_CASE(4) DIA_CASE(5) DIA_CASE(6) DIA_CASE(7)
       DIA_CASE(8)
@@ -860,15 +876,13 @@ extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double ato
       RET(launch_spmv_dot(ctx, p, ap, sc + SC_PAP));
       if (multi) RET(b200_allreduce_sum(ctx, sc + SC_PAP, 1));
       if (k == todo - 1) {
-        LAUNCH(ctx, k_update_xr<true>, g2, PCG_T, 0, xt, r, p, ap, d, n, sc, in, out, part, ticket,
-               sc);
+        LAUNCH(ctx, k_update_r<true>, g2, PCG_T, 0, r, ap, d, n, sc, in, out, part, ticket, sc);
         if (multi) RET(b200_allreduce_sum(ctx, sc + out, 2));
       } else {
-        LAUNCH(ctx, k_update_xr<false>, g2, PCG_T, 0, xt, r, p, ap, d, n, sc, in, out, part,
-               ticket, sc);
+        LAUNCH(ctx, k_update_r<false>, g2, PCG_T, 0, r, ap, d, n, sc, in, out, part, ticket, sc);
         if (multi) RET(b200_allreduce_sum(ctx, sc + out, 1));
       }
-      LAUNCH(ctx, k_update_p, g2, PCG_T, 0, p, r, n, sc, in, out);
+      LAUNCH(ctx, k_update_xp, g2, PCG_T, 0, xt, p, r, n, sc, in, out);
     }
     const int cur = 2 * (int)(it & 1);      // pair written by the last K_B
     CK(cudaMemcpyAsync(ctx->scal_h, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost,
@@ -957,10 +971,10 @@ extern "C" int b200_time_kernel(b200_ctx* ctx, int which, int reps, double* ms_a
     switch (which) {
       case 0: RET(launch_spmv_dot(ctx, p, ap, sc + SC_AUX2)); break;
       case 1:
-        LAUNCH(ctx, k_update_xr<true>, g2, PCG_T, 0, xt, r, p, ap, d, n, sc, SC_AUX0, SC_AUX1,
-               part, ticket, sc);
+        LAUNCH(ctx, k_update_r<true>, g2, PCG_T, 0, r, ap, d, n, sc, SC_AUX0, SC_AUX1, part,
+               ticket, sc);
         break;
-      case 2: LAUNCH(ctx, k_update_p, g2, PCG_T, 0, p, r, n, sc, SC_AUX0, SC_AUX1); break;
+      case 2: LAUNCH(ctx, k_update_xp, g2, PCG_T, 0, xt, p, r, n, sc, SC_AUX0, SC_AUX1); break;
       case 3:
         RET(b200_spmv_csr_raw(ctx, ctx->sys_indptr.as<int>(), ctx->sys_indices.as<int>(),
                               ctx->sys_data.as<double>(), n, ctx->row_begin, p - 0, ap));
