@@ -104,7 +104,8 @@ struct b200_ctx {
   int fmt = B200_FMT_NONE;
   int force_fmt = 0;
   bool unit_diag = true;
-  int64_t pad = 0;            // halo/padding entries on each side of vectors
+  int64_t pad = 0;            // padding entries on each side of vectors (>= halo)
+  int64_t halo = 0;           // entries actually exchanged with each neighbour rank
   DevBuf sc;                  // s_i = d_i^-1/2, padded layout
   DevBuf dexp;                // explicit diagonal when !unit_diag
   DiaPack dia{};
@@ -229,6 +230,7 @@ enum { FLAG_INDEX = 0, FLAG_NONFINITE = 1, FLAG_NONPOS_DIAG = 2, FLAG_OVERFLOW =
 int b200_halo_exchange(b200_ctx* ctx, double* base);           // padded vector
 int b200_allreduce_sum(b200_ctx* ctx, double* dev, int count); // in place, fp64
 int b200_allreduce_max_host(b200_ctx* ctx, int64_t* v);
+void b200_comm_release(b200_ctx* ctx);
 // solver.cu
 int b200_linearize(b200_ctx* ctx, const double* x);
 int b200_residual_norms(b200_ctx* ctx, const double* x, double* res2, double* x2);

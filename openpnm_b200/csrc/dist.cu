@@ -90,6 +90,11 @@ extern "C" int b200_comm_init(b200_ctx* ctx, int nranks, int rank, const void* i
   return B200_OK;
 }
 
+void b200_comm_release(b200_ctx* ctx) {
+  if (ctx->nccl && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)ctx->nccl);
+  ctx->nccl = nullptr;
+}
+
 extern "C" int b200_set_slab(b200_ctx* ctx, int64_t n_global, int64_t row_begin, int64_t row_end) {
   if (!ctx || row_begin < 0 || row_end > n_global || row_begin >= row_end) return B200_ERR_ARG;
   ctx->n_global = n_global;
@@ -101,18 +106,18 @@ extern "C" int b200_set_slab(b200_ctx* ctx, int64_t n_global, int64_t row_begin,
 
 // base points at the start of a padded vector [pad | n | pad]
 int b200_halo_exchange(b200_ctx* ctx, double* base) {
-  if (ctx->nranks == 1 || ctx->pad == 0) return B200_OK;
+  if (ctx->nranks == 1 || ctx->halo == 0) return B200_OK;
   ncclComm_t comm = (ncclComm_t)ctx->nccl;
-  const int64_t pad = ctx->pad, n = ctx->n;
+  const int64_t pad = ctx->pad, h = ctx->halo, n = ctx->n;
   double* own = base + pad;
   NCK(g_nccl.GroupStart());
   if (ctx->rank > 0) {
-    NCK(g_nccl.Send(own, (size_t)pad, ncclDouble, ctx->rank - 1, comm, ctx->stream));
-    NCK(g_nccl.Recv(base, (size_t)pad, ncclDouble, ctx->rank - 1, comm, ctx->stream));
+    NCK(g_nccl.Send(own, (size_t)h, ncclDouble, ctx->rank - 1, comm, ctx->stream));
+    NCK(g_nccl.Recv(own - h, (size_t)h, ncclDouble, ctx->rank - 1, comm, ctx->stream));
   }
   if (ctx->rank < ctx->nranks - 1) {
-    NCK(g_nccl.Send(own + n - pad, (size_t)pad, ncclDouble, ctx->rank + 1, comm, ctx->stream));
-    NCK(g_nccl.Recv(own + n, (size_t)pad, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+    NCK(g_nccl.Send(own + n - h, (size_t)h, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+    NCK(g_nccl.Recv(own + n, (size_t)h, ncclDouble, ctx->rank + 1, comm, ctx->stream));
   }
   NCK(g_nccl.GroupEnd());
   return B200_OK;

@@ -388,12 +388,19 @@ static int prepare_operator(b200_ctx* ctx) {
     FAIL(B200_ERR_ARG, "DIA format forced but the matrix has more than %d diagonals",
          B200_MAX_DIAGS);
   if (ctx->force_fmt == B200_FMT_DIA) want_dia = true;
-  int64_t pad = (want_dia || ctx->nranks > 1) ? tab.maxband : 0;
-  RET(b200_allreduce_max_host(ctx, &pad));          // every rank uses the same halo width
-  pad = (pad + 31) / 32 * 32;
-  if (ctx->nranks > 1 && pad > n)
-    FAIL(B200_ERR_ARG, "slab of %lld rows is thinner than the matrix half-bandwidth %lld",
-         (long long)n, (long long)pad);
+  int64_t halo = (want_dia || ctx->nranks > 1) ? tab.maxband : 0;
+  RET(b200_allreduce_max_host(ctx, &halo));         // every rank uses the same halo width
+  int64_t nmin = n;
+  if (ctx->nranks > 1) {
+    int64_t neg = -n;
+    RET(b200_allreduce_max_host(ctx, &neg));
+    nmin = -neg;
+  }
+  if (ctx->nranks > 1 && halo > nmin)
+    FAIL(B200_ERR_ARG, "a slab of %lld rows is thinner than the matrix half-bandwidth %lld",
+         (long long)nmin, (long long)halo);
+  const int64_t pad = (halo + 31) / 32 * 32;        // allocation keeps 256-byte alignment
+  ctx->halo = halo;
   ctx->pad = pad;
   const size_t vbytes = (size_t)(n + 2 * pad) * sizeof(double);
 
