@@ -277,11 +277,11 @@ def gpu_arm(args):
     nnz_loc = nnz
     b_spmv = 12 * nnz_loc + 4 * (n_loc + 1) + 16 * n_loc          # SURVEY 8d CSR model
     b_iter = b_spmv + 88 * n_loc
-    if fmt_code == 2:
-        fmt_spmv = (nd + 2) * 8 * n_loc
-    else:
-        fmt_spmv = 12 * (nnz_loc - n_loc) + 4 * n_loc + 16 * n_loc
-    fmt_iter = fmt_spmv + 24 * n_loc + 40 * n_loc
+    if fmt_code == 2:          # nd value arrays + p + r read, Ap written
+        fmt_spmv = (nd + 3) * 8 * n_loc
+    else:                      # off-diagonal (val, col) pairs + row pointers + p, r, Ap
+        fmt_spmv = 12 * (nnz_loc - n_loc) + 4 * n_loc + 24 * n_loc
+    fmt_iter = fmt_spmv + 56 * n_loc          # K_BC: read x,r,p,Ap, write x,r,p
     peak, peak_src = peaks()
     ms_iter = float(np.mean(t_solve_ms)) / max(cg_iters, 1)
 
@@ -339,19 +339,19 @@ def gpu_arm(args):
             "conservation": abs(q_in + q_out) / abs(q_in) if q_in else None,
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "K_A SpMV+dot (k_dia_spmv_dot / "
+            "roofline": {"bound": "hbm", "kernel": "K_A SpMV + 3 dots (k_dia_spmv_dot / "
                          "k_csr_stream_spmv_dot)", "achieved": b_spmv / (t_ka * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s",
                          "frac": b_spmv / (t_ka * 1e-3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_src, "ms": t_ka,
                          "algorithmic_bytes": int(b_spmv), "format_bytes": int(fmt_spmv),
                          "frac_format_bytes": fmt_spmv / (t_ka * 1e-3) / 1e9 / peak},
-            "roofline_iter": {"bound": "hbm", "kernel": "one PCG iteration (K_A + K_B + K_C)",
+            "roofline_iter": {"bound": "hbm", "kernel": "one PCG iteration (K_A SpMV + dots, K_BC fused x/r/p update + r.r)",
                               "achieved": b_iter / (ms_iter * 1e-3) / 1e9, "peak": peak,
                               "unit": "GB/s", "frac": b_iter / (ms_iter * 1e-3) / 1e9 / peak,
                               "algorithmic_bytes": int(b_iter), "format_bytes": int(fmt_iter),
                               "frac_format_bytes": fmt_iter / (ms_iter * 1e-3) / 1e9 / peak,
-                              "ms": ms_iter, "kernel_ms": {"K_A": t_ka, "K_B": t_kb, "K_C": t_kc}},
+                              "ms": ms_iter, "kernel_ms": {"K_A": t_ka, "K_BC": t_kb, "K_BC_with_true_norm": t_kc}},
         }
         if e2e:
             line["e2e"] = e2e

@@ -50,19 +50,20 @@ struct DiaPack {
   const double* v[B200_MAX_DIAGS];  // each points at row 0 of the owned range
 };
 
-// device-side scalar slots of the PCG (all doubles, in ctx->scal)
-// pair p (iteration parity): [2p] = r.r, [2p+1] = sum d_i r_i^2 (the unscaled
-// residual norm^2); the pair is contiguous so one all-reduce covers both.
+// device-side scalar slots of the PCG (all doubles, in ctx->scal).
+// Two ping-pong groups of five, indexed by iteration parity; a group is the
+// unit of the single all-reduce an iteration makes:
+//   [0] p.Ap  [1] r.Ap  [2] Ap.Ap      written by K_A of iteration k
+//   [3] r.r   [4] sum d_i r_i^2        written by K_BC of iteration k-1
 enum {
-  SC_RR0 = 0,
-  SC_TRUE0 = 1,
-  SC_RR1 = 2,
-  SC_TRUE1 = 3,
-  SC_PAP = 4,   // p.Ap
-  SC_BNORM = 5, // ||b||^2
-  SC_AUX0 = 6,
-  SC_AUX1 = 7,
-  SC_AUX2 = 8,
+  SC_GROUP = 5,
+  G_PAP = 0, G_RAP = 1, G_APAP = 2, G_RR = 3, G_TRUE = 4,
+  SC_BNORM = 10, // ||b||^2
+  SC_AUX0 = 11,
+  SC_AUX1 = 12,
+  SC_AUX2 = 13,
+  SC_AUX3 = 14,
+  SC_AUX4 = 15,
   SC_COUNT = 16
 };
 

@@ -47,8 +47,8 @@ def run(n, fmt, rtol=1e-10):
           f"pcg={ts:.1f}ms (setup {st['t_setup_ms']:.1f} solve {st['t_solve_ms']:.1f}) iters={it} "
           f"info={info} relres={rel:.2e} ms/iter={st['t_solve_ms']/max(it,1):.4f} "
           f"DOFit/s={Np*it/(ts*1e-3):.3e} model GB/s iter={model_iter*it/(st['t_solve_ms']*1e-3)/1e9:.0f}")
-    for which, name, bytes_model in ((0, "K_A spmv+dot", model_spmv), (1, "K_B r", 24 * Np),
-                                     (2, "K_C x,p", 40 * Np), (3, "K3 csr spmv", model_spmv)):
+    for which, name, bytes_model in ((0, "K_A spmv+dot", model_spmv), (1, "K_BC", 56 * Np),
+                                     (2, "K_BC exact", 64 * Np), (3, "K3 csr spmv", model_spmv)):
         ms = ctx.time_kernel(which, 20)
         print(f"    {name:14s} {ms*1e3:9.1f} us   model {bytes_model/ (ms*1e-3)/1e9:8.0f} GB/s")
     rl = ctx.rate_pores(x, pn.pores("left")).sum().item()

@@ -72,4 +72,10 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        import traceback
+        msg = traceback.format_exc().strip().splitlines()
+        print(f"WORKER-ERR rank={os.environ.get('RANK')}: " + " | ".join(msg[-6:]), flush=True)
+        os._exit(1)

@@ -31,5 +31,6 @@ def test_slab_solve_multi_gpu(world):
            f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port",
            str(29600 + world), os.path.join(ROOT, "tests", "dist_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    errs = [ln for ln in r.stdout.splitlines() if "WORKER-ERR" in ln]
+    assert r.returncode == 0, "\n".join(errs[:4]) + r.stderr[-1500:]
     assert r.stdout.count("dist ok") == 6
