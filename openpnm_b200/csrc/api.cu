@@ -20,6 +20,9 @@ extern "C" int b200_create(int device, b200_ctx** out) {
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreate(&ctx->ev2) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_vec_ready, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_halo_done, cudaEventDisableTiming) != cudaSuccess ||
       cudaMallocHost(&ctx->scal_h, SC_COUNT * sizeof(double)) != cudaSuccess ||
       cudaMallocHost(&ctx->flags_h, FLAG_COUNT * sizeof(int)) != cudaSuccess) {
     delete ctx;
@@ -49,6 +52,9 @@ extern "C" int b200_destroy(b200_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+  if (ctx->ev_vec_ready) cudaEventDestroy(ctx->ev_vec_ready);
+  if (ctx->ev_halo_done) cudaEventDestroy(ctx->ev_halo_done);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return B200_OK;

@@ -72,6 +72,8 @@ struct b200_ctx {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  cudaStream_t comm_stream = nullptr;   // halo exchange overlapping the interior SpMV
+  cudaEvent_t ev_vec_ready = nullptr, ev_halo_done = nullptr;
   std::string err;
   bool debug = false;         // B200_DEBUG=1: trace the host loops on stderr
   int64_t launches = 0;
@@ -192,7 +194,8 @@ __device__ __forceinline__ double block_sum(double v) {
 // order and writes out[k].  No floating-point atomics anywhere.
 template <int NV>
 __device__ __forceinline__ void grid_sum_finalize(const double (&v)[NV], double* part,
-                                                  unsigned* ticket, double* const (&out)[NV]) {
+                                                  unsigned* ticket, double* const (&out)[NV],
+                                                  bool accumulate = false) {
   __shared__ bool is_last;
   double bs[NV];
 #pragma unroll
@@ -213,7 +216,7 @@ __device__ __forceinline__ void grid_sum_finalize(const double (&v)[NV], double*
       for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x)
         s += __ldcg(&part[(size_t)k * gridDim.x + i]);
       s = block_sum(s);
-      if (threadIdx.x == 0) *out[k] = s;
+      if (threadIdx.x == 0) *out[k] = accumulate ? *out[k] + s : s;
     }
   }
 }
@@ -229,6 +232,8 @@ enum { FLAG_INDEX = 0, FLAG_NONFINITE = 1, FLAG_NONPOS_DIAG = 2, FLAG_OVERFLOW =
 
 // dist.cu (no-ops when nranks == 1)
 int b200_halo_exchange(b200_ctx* ctx, double* base);           // padded vector
+int b200_halo_exchange_begin(b200_ctx* ctx, double* base);     // on comm_stream
+int b200_halo_exchange_end(b200_ctx* ctx);                     // stream waits for it
 int b200_allreduce_sum(b200_ctx* ctx, double* dev, int count); // in place, fp64
 int b200_allreduce_max_host(b200_ctx* ctx, int64_t* v);
 void b200_comm_release(b200_ctx* ctx);

@@ -105,21 +105,42 @@ extern "C" int b200_set_slab(b200_ctx* ctx, int64_t n_global, int64_t row_begin,
 }
 
 // base points at the start of a padded vector [pad | n | pad]
-int b200_halo_exchange(b200_ctx* ctx, double* base) {
-  if (ctx->nranks == 1 || ctx->halo == 0) return B200_OK;
+static int halo_on(b200_ctx* ctx, double* base, cudaStream_t st) {
   ncclComm_t comm = (ncclComm_t)ctx->nccl;
   const int64_t pad = ctx->pad, h = ctx->halo, n = ctx->n;
   double* own = base + pad;
   NCK(g_nccl.GroupStart());
   if (ctx->rank > 0) {
-    NCK(g_nccl.Send(own, (size_t)h, ncclDouble, ctx->rank - 1, comm, ctx->stream));
-    NCK(g_nccl.Recv(own - h, (size_t)h, ncclDouble, ctx->rank - 1, comm, ctx->stream));
+    NCK(g_nccl.Send(own, (size_t)h, ncclDouble, ctx->rank - 1, comm, st));
+    NCK(g_nccl.Recv(own - h, (size_t)h, ncclDouble, ctx->rank - 1, comm, st));
   }
   if (ctx->rank < ctx->nranks - 1) {
-    NCK(g_nccl.Send(own + n - h, (size_t)h, ncclDouble, ctx->rank + 1, comm, ctx->stream));
-    NCK(g_nccl.Recv(own + n, (size_t)h, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+    NCK(g_nccl.Send(own + n - h, (size_t)h, ncclDouble, ctx->rank + 1, comm, st));
+    NCK(g_nccl.Recv(own + n, (size_t)h, ncclDouble, ctx->rank + 1, comm, st));
   }
   NCK(g_nccl.GroupEnd());
+  return B200_OK;
+}
+
+int b200_halo_exchange(b200_ctx* ctx, double* base) {
+  if (ctx->nranks == 1 || ctx->halo == 0) return B200_OK;
+  return halo_on(ctx, base, ctx->stream);
+}
+
+// Split form: the exchange runs on comm_stream while the caller's stream
+// computes the rows that do not read the halo; _end makes the stream wait.
+int b200_halo_exchange_begin(b200_ctx* ctx, double* base) {
+  if (ctx->nranks == 1 || ctx->halo == 0) return B200_OK;
+  CK(cudaEventRecord(ctx->ev_vec_ready, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_vec_ready, 0));
+  RET(halo_on(ctx, base, ctx->comm_stream));
+  CK(cudaEventRecord(ctx->ev_halo_done, ctx->comm_stream));
+  return B200_OK;
+}
+
+int b200_halo_exchange_end(b200_ctx* ctx) {
+  if (ctx->nranks == 1 || ctx->halo == 0) return B200_OK;
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo_done, 0));
   return B200_OK;
 }
 

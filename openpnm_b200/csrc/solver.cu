@@ -521,11 +521,16 @@ __global__ void __launch_bounds__(PCG_T) k_dia_spmv_dot(DiaPack A, const double*
                                                         const double* __restrict__ rv,
                                                         const double* __restrict__ dexp,
                                                         double* __restrict__ ap, int64_t n,
-                                                        double* part, unsigned* ticket,
-                                                        double* out_pap) {
+                                                        int64_t lo0, int64_t hi0, int64_t lo1,
+                                                        int accumulate, double* part,
+                                                        unsigned* ticket, double* out_pap) {
+  // rows [lo0, hi0) and [lo1, n): the whole range (lo1 = n) or the two halo-
+  // reading edges of a slab (hi0 = halo, lo1 = n - halo)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t len0 = hi0 - lo0, total = len0 + (n - lo1);
   double dot = 0.0, dot2 = 0.0, dotr = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
+    const int64_t i = q < len0 ? lo0 + q : lo1 + (q - len0);
     const double pi = p[i];
     double acc = UNIT ? pi : dexp[i] * pi;
 #pragma unroll
@@ -541,7 +546,7 @@ __global__ void __launch_bounds__(PCG_T) k_dia_spmv_dot(DiaPack A, const double*
   }
   double v[3] = {dot, dotr, dot2};
   double* o[3] = {out_pap + G_PAP, out_pap + G_RAP, out_pap + G_APAP};
-  grid_sum_finalize<3>(v, part, ticket, o);
+  grid_sum_finalize<3>(v, part, ticket, o, accumulate != 0);
 }
 
 // ---- K_A (CSR-stream): vals/cols streamed coalesced into shared memory as
@@ -741,13 +746,20 @@ static int pcg_grid(b200_ctx* ctx, int per_thread) {
   return (int)want;
 }
 
+// part = 0: all rows; 1: interior rows only (no halo read); 2: the two edges,
+// accumulated onto the sums part 1 left (DIA only; CSR always runs whole)
 static int launch_spmv_dot(b200_ctx* ctx, const double* p_owned, const double* r_owned,
-                           double* ap_owned, double* out) {
+                           double* ap_owned, double* out, int part_sel = 0) {
   double* part = ctx->w_part.as<double>();
   unsigned* ticket = ctx->w_ticket.as<unsigned>();
   const double* dexp = ctx->dexp.as<double>();
   const int64_t n = ctx->n;
   if (ctx->fmt == B200_FMT_DIA) {
+    int64_t lo0 = 0, hi0 = n, lo1 = n;
+    if (part_sel == 1) { lo0 = ctx->halo; hi0 = n - ctx->halo; }
+    if (part_sel == 2) { lo0 = 0; hi0 = ctx->halo; lo1 = n - ctx->halo; }
+    const int64_t rows = (hi0 - lo0) + (n - lo1);
+    const int acc = part_sel == 2 ? 1 : 0;
     // one full wave: resident CTAs per SM (from the occupancy calculator, the
     // register count differs per ND) x SM count, grid-stride inside
 #define DIA_CASE(ND)                                                                       \
@@ -758,10 +770,11 @@ static int launch_spmv_dot(b200_ctx* ctx, const double* p_owned, const double* r
                                                        PCG_T, 0));                         \
       if (occ < 1) occ = 1;                                                                \
     }                                                                                      \
-    int64_t g = (n + PCG_T - 1) / PCG_T;                                                   \
+    int64_t g = (rows + PCG_T - 1) / PCG_T;                                                \
     if (g > (int64_t)occ * ctx->num_sms) g = (int64_t)occ * ctx->num_sms;                  \
+    if (g < 1) g = 1;                                                                      \
     LAUNCH(ctx, (k_dia_spmv_dot<ND, true>), (int)g, PCG_T, 0, ctx->dia, p_owned, r_owned,  \
-           dexp, ap_owned, n, part, ticket, out);                                                \
+           dexp, ap_owned, n, lo0, hi0, lo1, acc, part, ticket, out);                      \
   } break;
     switch (ctx->dia.nd) {
       DIA_CASE(1) DIA_CASE(2) DIA_CASE(3) DIA_CASE(4) DIA_CASE(5) DIA_CASE(6) DIA_CASE(7)
@@ -883,8 +896,16 @@ extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double ato
     for (int64_t k = 0; k < todo; ++k, ++it) {
       double* gin = sc + SC_GROUP * (int)(it & 1);
       double* gout = sc + SC_GROUP * (int)((it + 1) & 1);
-      if (multi) RET(b200_halo_exchange(ctx, ctx->vp.as<double>()));
-      RET(launch_spmv_dot(ctx, p, r, ap, gin));
+      if (multi && ctx->fmt == B200_FMT_DIA && n > 4 * ctx->halo) {
+        // interior rows while the halo windows of p travel; then the two edges
+        RET(b200_halo_exchange_begin(ctx, ctx->vp.as<double>()));
+        RET(launch_spmv_dot(ctx, p, r, ap, gin, 1));
+        RET(b200_halo_exchange_end(ctx));
+        RET(launch_spmv_dot(ctx, p, r, ap, gin, 2));
+      } else {
+        if (multi) RET(b200_halo_exchange(ctx, ctx->vp.as<double>()));
+        RET(launch_spmv_dot(ctx, p, r, ap, gin));
+      }
       if (multi) RET(b200_allreduce_sum(ctx, gin, rr_is_global ? 3 : SC_GROUP));
       rr_is_global = false;
       if (k == todo - 1)
