@@ -216,6 +216,7 @@ def gpu_arm(args):
 
     ss = bdist.SlabSolver(Np, rb, re, device=local, fmt=args.fmt)
     ctx = ss.ctx
+    p2p = False
     conns_d, g_d, bcv_d = ctx.to_device(conns_h), ctx.to_device(g_h), ctx.to_device(bcv_h)
     left_d = left[(left >= rb) & (left < re)]
     right_d = right[(right >= rb) & (right < re)]
@@ -231,6 +232,9 @@ def gpu_arm(args):
         x, it, rel, info = ss.solve(rtol=RTOL)
         return x, it, rel, info, nnz
 
+    if world > 1 and not args.no_p2p:
+        ss.assemble(conns_d, g_d, bcv_d, None)
+        p2p = ss.enable_p2p()        # CUDA-IPC mapping of the peers: collectives fused in-kernel
     for _ in range(args.warmup):
         x, it, rel, info, nnz = device_step()
     barrier()
@@ -332,7 +336,9 @@ def gpu_arm(args):
             "config": workload_config(n, Np, Nt, {
                 "nnz": nnz_global, "cg_iters": cg_iters, "relres": rel, "info": info,
                 "format": {1: "csr", 2: f"dia{nd}-sym"}.get(fmt_code, "?"),
-                "parallelism": f"slab{world}", "host_prep_s": round(t_host, 1)}),
+                "parallelism": f"slab{world}", "host_prep_s": round(t_host, 1),
+                "comm": ("none" if world == 1 else
+                         "in-kernel peer stores over NVLink (CUDA IPC)" if p2p else "NCCL")}),
             "time_to_solve_s": ms_step * 1e-3,
             "ms_per_cg_iter": ms_iter,
             "rate_inlet": q_in, "rate_outlet": q_out,
@@ -374,6 +380,7 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=100)
     ap.add_argument("--fmt", default="auto", choices=["auto", "csr", "dia"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

@@ -197,6 +197,16 @@ int b200_nccl_unique_id(void* id128_h);
 int b200_comm_init(b200_ctx* ctx, int nranks, int rank, const void* id128_h);
 int b200_set_slab(b200_ctx* ctx, int64_t n_global, int64_t row_begin,
                   int64_t row_end);
+/* Fused communication over NVLink peer memory (optional, lattice/DIA operator):
+ * after b200_pcg_prepare every rank exports two 64-byte CUDA-IPC handles
+ * (its mailbox block and its direction vector p); the host all-gathers them
+ * together with every rank's row count and attaches.  From then on the PCG
+ * iteration makes no NCCL call: K_A's last block stores its dot products into
+ * every peer's mailbox, K_BC sums the mailboxes in rank order and stores the
+ * edge entries of the new p straight into the neighbours' halo windows.     */
+int b200_p2p_export(b200_ctx* ctx, void* handles128_h);
+int b200_p2p_attach(b200_ctx* ctx, const void* all_handles_h, const int64_t* all_rows_h);
+int b200_p2p_disable(b200_ctx* ctx);
 
 #ifdef __cplusplus
 }

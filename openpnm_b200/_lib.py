@@ -77,6 +77,9 @@ SIGNATURES = {
     "b200_nccl_unique_id": (C.c_int, [_p]),
     "b200_comm_init": (C.c_int, [_p, C.c_int, C.c_int, _p]),
     "b200_set_slab": (C.c_int, [_p, _i64, _i64, _i64]),
+    "b200_p2p_export": (C.c_int, [_p, _p]),
+    "b200_p2p_attach": (C.c_int, [_p, _p, _p]),
+    "b200_p2p_disable": (C.c_int, [_p]),
 }
 
 _LIB = None

@@ -67,6 +67,24 @@ enum {
   SC_COUNT = 16
 };
 
+// Peer-to-peer state of the fused-communication PCG (p2p.cu): mailboxes and
+// halo windows of the neighbour ranks mapped through CUDA IPC over NVLink.
+struct P2PState {
+  bool ready = false;
+  void* mem = nullptr;                 // local: mailboxes + flags (one cudaMalloc, IPC-exported)
+  double* mbox = nullptr;              // [2 parities][8 ranks][8 doubles]
+  unsigned long long* flags = nullptr; // [0] halo from rank-1, [1] halo from rank+1, [2] error
+  double* peer_mbox[8] = {};
+  unsigned long long* peer_flags[8] = {};
+  double* peer_vp[8] = {};
+  void* opened[16] = {};
+  int n_opened = 0;
+  void* vp_at_attach = nullptr;
+  int64_t pad_at_attach = 0, halo_at_attach = 0;
+  int64_t n_of[8] = {};
+  unsigned long long seq = 0;
+};
+
 struct b200_ctx {
   int device = 0;
   int num_sms = 148;
@@ -82,6 +100,7 @@ struct b200_ctx {
   int64_t n_global = 0, row_begin = 0, row_end = 0, n = 0;
   int nranks = 1, rank = 0;
   void* nccl = nullptr;  // ncclComm_t
+  P2PState p2p;
 
   // pure Laplacian, canonical CSR of the owned rows (global column ids)
   DevBuf pure_indptr, pure_indices, pure_data, pure_diag;
@@ -237,6 +256,12 @@ int b200_halo_exchange_end(b200_ctx* ctx);                     // stream waits f
 int b200_allreduce_sum(b200_ctx* ctx, double* dev, int count); // in place, fp64
 int b200_allreduce_max_host(b200_ctx* ctx, int64_t* v);
 void b200_comm_release(b200_ctx* ctx);
+// p2p.cu
+void b200_p2p_release(b200_ctx* ctx);
+bool b200_p2p_usable(b200_ctx* ctx);
+int b200_p2p_iteration(b200_ctx* ctx, double* gin, double* gout, bool true_norm, bool wait_halo,
+                       bool rr_is_global, const double* d);
+int b200_p2p_check(b200_ctx* ctx);
 // solver.cu
 int b200_linearize(b200_ctx* ctx, const double* x);
 int b200_residual_norms(b200_ctx* ctx, const double* x, double* res2, double* x2);

@@ -889,6 +889,8 @@ extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double ato
   // all-reduced on their own for the host); otherwise they ride along with the
   // K_A sums in the single per-iteration all-reduce
   bool rr_is_global = true;
+  const bool p2p = multi && b200_p2p_usable(ctx);
+  bool p_halo_stale = true;      // p = r from k_pcg_resid: its halo was not pushed by K_BC
   while (!done) {
     if (it >= maxiter) break;
     int64_t todo = batch;
@@ -896,6 +898,15 @@ extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double ato
     for (int64_t k = 0; k < todo; ++k, ++it) {
       double* gin = sc + SC_GROUP * (int)(it & 1);
       double* gout = sc + SC_GROUP * (int)((it + 1) & 1);
+      if (p2p) {
+        // fused communication over NVLink peer memory (p2p.cu): the only NCCL
+        // call left is the halo of a p that did not come out of K_BC
+        if (p_halo_stale) RET(b200_halo_exchange(ctx, ctx->vp.as<double>()));
+        RET(b200_p2p_iteration(ctx, gin, gout, k == todo - 1, !p_halo_stale, rr_is_global, d));
+        p_halo_stale = false;
+        rr_is_global = false;
+        continue;
+      }
       if (multi && ctx->fmt == B200_FMT_DIA && n > 4 * ctx->halo) {
         // interior rows while the halo windows of p travel; then the two edges
         RET(b200_halo_exchange_begin(ctx, ctx->vp.as<double>()));
@@ -921,6 +932,7 @@ extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double ato
     CK(cudaMemcpyAsync(ctx->scal_h, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost,
                        ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (p2p) RET(b200_p2p_check(ctx));
     true2 = ctx->scal_h[cur + G_TRUE];
     const double pap = ctx->scal_h[prv + G_PAP];
     const double rrn = ctx->scal_h[cur + G_RR];
@@ -948,6 +960,7 @@ extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double ato
       ++restarts;
       prev_true2 = true2;
       batch = 8;
+      p_halo_stale = true;
       continue;
     }
     // choose the next batch from the observed convergence rate

@@ -153,7 +153,8 @@ class SlabSolver:
         self.ctx = Context(device)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
-        self.ctx.set_format({"auto": 0, "csr": _lib.FMT_CSR, "dia": _lib.FMT_DIA}[fmt])
+        self._fmt = {"auto": 0, "csr": _lib.FMT_CSR, "dia": _lib.FMT_DIA}[fmt]
+        self.ctx.set_format(self._fmt)
         if self.world > 1:
             buf = (C.c_ubyte * 128)()
             if self.rank == 0:
@@ -184,6 +185,44 @@ class SlabSolver:
             ctx.set_diag_mean(float(t[0] / t[1]))
         f, nnz_sys = ctx.apply_bcs(bc_value, bc_rate)
         return f, nnz, nnz_sys
+
+    def enable_p2p(self):
+        """Map the peers' mailboxes and direction vectors (CUDA IPC over NVLink) so
+        the PCG iteration communicates from inside its kernels (csrc/p2p.cu).
+        Call after assemble(); returns False when not applicable (single rank,
+        irregular operator)."""
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        ctx = self.ctx
+        if self.world < 2 or self.world > 8:
+            return False
+        ctx.pcg_prepare(self._fmt)
+        fmt, _ = ctx.pcg_format()
+        ok = torch.tensor([1 if fmt == _lib.FMT_DIA else 0], dtype=torch.int64)
+        dev = ctx.tdev if dist.get_backend() == "nccl" else torch.device("cpu")
+        ok = ok.to(dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            return False
+        buf = (C.c_ubyte * 128)()
+        ctx._ck(ctx.lib.b200_p2p_export(ctx._h, C.cast(buf, C.c_void_p)))
+        mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine)
+        rows = torch.tensor([self.row_end - self.row_begin], dtype=torch.int64, device=dev)
+        allr = [torch.empty_like(rows) for _ in range(self.world)]
+        dist.all_gather(allr, rows)
+        raw = b"".join(bytes(t.cpu().tolist()) for t in allh)
+        hbuf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        rbuf = (C.c_int64 * self.world)(*[int(t.item()) for t in allr])
+        ctx._ck(ctx.lib.b200_p2p_attach(ctx._h, C.cast(hbuf, C.c_void_p),
+                                        C.cast(rbuf, C.c_void_p)))
+        dist.barrier()
+        return True
+
+    def disable_p2p(self):
+        self.ctx._ck(self.ctx.lib.b200_p2p_disable(self.ctx._h))
 
     def solve(self, rtol=1e-10, maxiter=0, x0=None):
         return self.ctx.pcg(x0=x0, rtol=rtol, maxiter=maxiter)

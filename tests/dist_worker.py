@@ -48,12 +48,23 @@ def main():
             assert np.array_equal(L.indptr, Mloc.indptr), "slab indptr differs"
             assert np.array_equal(L.indices, Mloc.indices), "slab indices differ"
             np.testing.assert_allclose(L.data, Mloc.data, rtol=1e-12, atol=0)
+            xr, _ = oracle.spsolve(M, b)
             x_loc, it, rel, info = ss.solve(rtol=1e-13)
             assert info == 0, (info, it, rel)
             x = ss.gather(x_loc).cpu().numpy()
-            xr, _ = oracle.spsolve(M, b)
             err = np.max(np.abs(x - xr)) / np.max(np.abs(xr))
             assert err < 1e-8, (shape, fmt, err)
+            # same solve with the collectives fused into the kernels over peer memory
+            p2p = ss.enable_p2p() if world > 1 else False
+            if p2p:
+                x2_loc, it2, rel2, info2 = ss.solve(rtol=1e-13)
+                assert info2 == 0, (info2, it2, rel2)
+                x2 = ss.gather(x2_loc).cpu().numpy()
+                err2 = np.max(np.abs(x2 - xr)) / np.max(np.abs(xr))
+                assert err2 < 1e-8, (shape, fmt, "p2p", err2)
+                x3_loc, it3, _, _ = ss.solve(rtol=1e-13)          # repeatable bit for bit
+                assert it3 == it2 and bool((x3_loc == x2_loc).all())
+                it = (it, it2)
             xg = torch.from_numpy(x).to(ss.ctx.tdev)
             q = torch.tensor([ss.rate(xg, net["labels"]["left"]),
                               ss.rate(xg, net["labels"]["right"])], dtype=torch.float64,
@@ -64,7 +75,7 @@ def main():
             assert abs(float(q[0]) - qref) <= 1e-8 * abs(qref)
             if rank == 0:
                 print(f"dist ok shape={shape} fmt={fmt} world={world} iters={it} err={err:.2e} "
-                      f"fmtcode={ss.ctx.pcg_format()}", flush=True)
+                      f"p2p={p2p} fmtcode={ss.ctx.pcg_format()}", flush=True)
             ss.ctx.close()
     if world > 1:
         dist.barrier()
