@@ -210,7 +210,7 @@ struct OffTable {
   int maxband;
 };
 
-// distinct positive offsets (col - row) of the system matrix; integer CAS only
+// distinct |col - row| of the off-diagonals of the system matrix; integer CAS only
 __global__ void k_detect_offsets(const int* __restrict__ indptr, const int* __restrict__ indices,
                                  int64_t n, int64_t rb, OffTable* tab) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -221,8 +221,10 @@ __global__ void k_detect_offsets(const int* __restrict__ indptr, const int* __re
       const int64_t o64 = (int64_t)indices[e] - gi;
       const int ao = (int)(o64 < 0 ? -o64 : o64);
       if (ao > mymax) mymax = ao;
-      if (o64 <= 0) continue;
-      const int o = (int)o64;
+      if (o64 == 0) continue;
+      // |offset| of lower entries too: in a slab a lower entry may point below
+      // the owned rows while no owned row has the mirrored upper entry
+      const int o = ao;
       bool found = false;
       for (int k = 0; k < B200_MAX_DIAGS && !found; ++k) {
         int cur = tab->off[k];      // may be stale (L1): the CAS below is the truth

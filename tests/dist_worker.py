@@ -20,6 +20,7 @@ def main():
 
     rank, world, local = bdist.init_process_group()
     shapes = [(8, 5, 6), (13, 4, 7), (24, 24, 24)]
+    # (8,5,6) on 8 ranks: one-plane slabs, the slab next to the outlet has no upper x-entry
     for shape in shapes:
         for fmt in ("auto", "csr"):
             nx, ny, nz = shape
