@@ -19,19 +19,25 @@ def main():
     from oracle import oracle
 
     rank, world, local = bdist.init_process_group()
-    shapes = [(8, 5, 6), (13, 4, 7), (24, 24, 24)]
-    # (8,5,6) on 8 ranks: one-plane slabs, the slab next to the outlet has no upper x-entry
-    for shape in shapes:
+    # (8,5,6) on 8 ranks and the 'z' cases: one-plane slabs, some of which have x-couplings
+    # only downwards (no mirrored upper entry among the owned rows)
+    cases = [((8, 5, 6), "x"), ((13, 4, 7), "x"), ((24, 24, 24), "x"), ((2, 5, 6), "z"),
+             ((8, 3, 5), "z")]
+    for shape, bcdir in cases:
+        if shape[0] < world:
+            continue
         for fmt in ("auto", "csr"):
             nx, ny, nz = shape
             net = oracle.cubic_network(shape)
             Np, Nt = net["Np"], net["Nt"]
             g_all = 10.0 ** np.random.default_rng(3).uniform(-15, -12, Nt)
             bcv = np.full(Np, np.nan)
-            bcv[net["labels"]["left"]] = 2.0
-            bcv[net["labels"]["right"]] = 1.0
+            lo_lbl, hi_lbl, side = ("left", "right", "top") if bcdir == "x" else \
+                                   ("top", "bottom", "front")
+            bcv[net["labels"][lo_lbl]] = 2.0
+            bcv[net["labels"][hi_lbl]] = 1.0
             bcr = np.full(Np, np.nan)
-            bcr[net["labels"]["top"][5:9]] = 1e-13        # a few rate BCs too
+            bcr[net["labels"][side][5:9]] = 1e-13         # a few rate BCs too
             bcr[np.isfinite(bcv)] = np.nan
             rb, re = bdist.cubic_slab_ranges(shape, world)[rank]
             ids, conns = bdist.cubic_slab_throats(shape, rb // (ny * nz), re // (ny * nz))
@@ -67,12 +73,12 @@ def main():
                 assert it3 == it2 and bool((x3_loc == x2_loc).all())
                 it = (it, it2)
             xg = torch.from_numpy(x).to(ss.ctx.tdev)
-            q = torch.tensor([ss.rate(xg, net["labels"]["left"]),
-                              ss.rate(xg, net["labels"]["right"])], dtype=torch.float64,
+            q = torch.tensor([ss.rate(xg, net["labels"][lo_lbl]),
+                              ss.rate(xg, net["labels"][hi_lbl])], dtype=torch.float64,
                              device=ss.ctx.tdev)
             if world > 1:
                 dist.all_reduce(q)
-            qref = oracle.rate(net["conns"], g_all, xr, pores=net["labels"]["left"])[0]
+            qref = oracle.rate(net["conns"], g_all, xr, pores=net["labels"][lo_lbl])[0]
             assert abs(float(q[0]) - qref) <= 1e-8 * abs(qref)
             if rank == 0:
                 print(f"dist ok shape={shape} fmt={fmt} world={world} iters={it} err={err:.2e} "
