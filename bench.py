@@ -289,7 +289,8 @@ def gpu_arm(args):
     peak, peak_src = peaks()
     ms_iter = float(np.mean(t_solve_ms)) / max(cg_iters, 1)
 
-    # ---- e2e through the public API, host buffers, single GPU only
+    # ---- e2e through the public API with HOST buffers: every step copies its
+    # inputs from pinned host memory and reads the solution back
     e2e = None
     if world == 1:
         ph = b2.Phase(pn)
@@ -317,6 +318,35 @@ def gpu_arm(args):
                "d2h_bytes_per_step": int(8 * Np + 8 * left.size),
                "ms_per_step": 1e3 * t_e2e, "api": "openpnm_b200.StokesFlow.run + rate",
                "rate_inlet": float(qq)}
+    else:
+        # slab API (openpnm_b200.dist.SlabSolver): each rank uploads the throats of its
+        # slab + the BC array, assembles, solves and downloads its part of x
+        x_h = pinned_copy(np.zeros(re - rb))
+
+        def e2e_step():
+            ss.assemble(conns_h, g_h, bcv_h, None)
+            xl, it_, rel_, info_ = ss.solve(rtol=RTOL)
+            with torch.cuda.stream(ctx.stream):
+                torch.from_numpy(x_h).copy_(xl, non_blocking=True)
+            ctx.synchronize()
+            return it_
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_iters = [e2e_step() for _ in range(args.steps)]
+        barrier()
+        t_e2e = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64,
+                             device=ctx.tdev)
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        t_e2e = float(t_e2e.item())
+        nbytes = torch.tensor([float(conns_h.nbytes + g_h.nbytes + bcv_h.nbytes),
+                               float(x_h.nbytes)], dtype=torch.float64, device=ctx.tdev)
+        dist.all_reduce(nbytes)
+        e2e = {"value": Np * float(np.mean(e2e_iters)) / t_e2e, "unit": "DOF*iter/s",
+               "h2d_bytes_per_step": int(nbytes[0].item()),
+               "d2h_bytes_per_step": int(nbytes[1].item()), "ms_per_step": 1e3 * t_e2e,
+               "api": "openpnm_b200.dist.SlabSolver.assemble + solve, x to host (all ranks)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -16,6 +16,8 @@ extern "C" int b200_create(int device, b200_ctx** out) {
   ctx->device = device;
   const char* dbg = getenv("B200_DEBUG");
   ctx->debug = dbg && dbg[0] && dbg[0] != '0';
+  const char* ch = getenv("B200_KA_CHUNK");
+  if (ch && atoi(ch) >= 1 && atoi(ch) <= 64) ctx->ka_chunk = atoi(ch);
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||

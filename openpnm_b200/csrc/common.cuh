@@ -88,6 +88,7 @@ struct P2PState {
 struct b200_ctx {
   int device = 0;
   int num_sms = 148;
+  int ka_chunk = 2;           // 256-row tiles a K_A CTA takes at a time (B200_KA_CHUNK)
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaStream_t comm_stream = nullptr;   // halo exchange overlapping the interior SpMV

@@ -524,14 +524,19 @@ __global__ void __launch_bounds__(PCG_T) k_dia_spmv_dot(DiaPack A, const double*
                                                         const double* __restrict__ dexp,
                                                         double* __restrict__ ap, int64_t n,
                                                         int64_t lo0, int64_t hi0, int64_t lo1,
-                                                        int accumulate, double* part,
+                                                        int accumulate, int chunk, double* part,
                                                         unsigned* ticket, double* out_pap) {
   // rows [lo0, hi0) and [lo1, n): the whole range (lo1 = n) or the two halo-
   // reading edges of a slab (hi0 = halo, lo1 = n - halo)
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // a CTA takes CHUNK consecutive 256-row tiles at a time, so that the +-k_y
+  // neighbour reads of a tile fall into rows the same CTA (same L1) touches
   const int64_t len0 = hi0 - lo0, total = len0 + (n - lo1);
+  const int64_t tile = (int64_t)blockDim.x * chunk;
   double dot = 0.0, dot2 = 0.0, dotr = 0.0;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
+  for (int64_t base = (int64_t)blockIdx.x * tile; base < total; base += (int64_t)gridDim.x * tile)
+  for (int c = 0; c < chunk; ++c) {
+    const int64_t q = base + (int64_t)c * blockDim.x + threadIdx.x;
+    if (q >= total) break;
     const int64_t i = q < len0 ? lo0 + q : lo1 + (q - len0);
     const double pi = p[i];
     double acc = UNIT ? pi : dexp[i] * pi;
@@ -776,7 +781,7 @@ static int launch_spmv_dot(b200_ctx* ctx, const double* p_owned, const double* r
     if (g > (int64_t)occ * ctx->num_sms) g = (int64_t)occ * ctx->num_sms;                  \
     if (g < 1) g = 1;                                                                      \
     LAUNCH(ctx, (k_dia_spmv_dot<ND, true>), (int)g, PCG_T, 0, ctx->dia, p_owned, r_owned,  \
-           dexp, ap_owned, n, lo0, hi0, lo1, acc, part, ticket, out);                      \
+           dexp, ap_owned, n, lo0, hi0, lo1, acc, ctx->ka_chunk, part, ticket, out);                      \
   } break;
     switch (ctx->dia.nd) {
       DIA_CASE(1) DIA_CASE(2) DIA_CASE(3) DIA_CASE(4) DIA_CASE(5) DIA_CASE(6) DIA_CASE(7)
