@@ -85,6 +85,18 @@ int b200_build_laplacian(b200_ctx* ctx, const int64_t* conns, const double* g,
                          int64_t Np, int64_t Nt, int64_t row_begin,
                          int64_t row_end, int64_t* nnz);
 
+/* ------------------------------------------------- topology health check
+ * Replaces Transport._validate_topology_health (_transport.py:243-251) ->
+ * topotools.is_fully_connected (topotools/_topotools.py:993-1024): counts the
+ * connected clusters of the network and those that contain no pore with a
+ * boundary condition (NaN = no BC in bc_value / bc_rate, either may be NULL).
+ * The reference raises "Your network is clustered ..." when the second count
+ * is non-zero.                                                               */
+int b200_check_topology(b200_ctx* ctx, const int64_t* conns, int64_t Nt,
+                        int64_t Np, const double* bc_value,
+                        const double* bc_rate, int64_t* n_clusters,
+                        int64_t* n_without_bc);
+
 /* ------------------------------------------------ K2: boundary conditions
  * Replaces Transport._build_b + _apply_BCs (_transport.py:117-121,145-169).
  * bc_value / bc_rate: (Np,) f64 for ALL pores (global indexing), NaN = no BC;

@@ -194,10 +194,21 @@ class Transport(dict):
             if self.settings.get(k) is None:
                 raise Exception(f"'{k}' hasn't been defined on this algorithm")
 
-    def _validate_topology_health(self):
+    def _validate_topology_health(self, ctx=None):
         """Every cluster must touch a BC pore (_transport.py:243-251 ->
-        topotools.is_fully_connected, topotools/_topotools.py:993-1024); host
-        graph check with scipy's C connected_components (no LIL detour)."""
+        topotools.is_fully_connected, topotools/_topotools.py:993-1024).
+        With a device context the clusters are found on the GPU
+        (b200_check_topology: lock-free union-find over the throat list);
+        without one, scipy's C connected_components does the same on the host
+        (a check only -- nothing of the solve runs on the CPU)."""
+        msg = "Your network is clustered, making Ax = b ill-conditioned"
+        if ctx is not None:
+            conns = self._device_conns(ctx)
+            _, nbad = ctx.check_topology(conns, self.Np, self["pore.bc.value"],
+                                         self["pore.bc.rate"])
+            if nbad:
+                raise Exception(msg)
+            return
         import scipy.sparse as sprs
         from scipy.sparse import csgraph
         conns = np.asarray(self.network["throat.conns"])
@@ -210,7 +221,18 @@ class Transport(dict):
         touched = np.zeros(ncomp, dtype=bool)
         touched[labels[bc]] = True
         if not touched.all():
-            raise Exception("Your network is clustered, making Ax = b ill-conditioned")
+            raise Exception(msg)
+
+    def _device_conns(self, ctx):
+        """throat.conns on the device, uploaded once per (context, network)
+        unless caching is off."""
+        import torch
+        conns = np.asarray(self.network["throat.conns"], dtype=np.int64)
+        key = (id(ctx), conns.__array_interface__["data"][0], conns.shape[0])
+        if not self.settings["cache"] or getattr(self, "_conns_key", None) != key:
+            self._conns_dev = ctx.to_device(conns, torch.int64)
+            self._conns_key = key
+        return self._conns_dev
 
     # ------------------------------------------------------------- solve
     def _sources(self):
@@ -227,8 +249,7 @@ class Transport(dict):
         g = self._conductance()
         key = (id(ctx), id(self.network), g.__array_interface__["data"][0], g.size)
         if not (self.settings["cache"] and self._cache_key == key):
-            conns = np.asarray(self.network["throat.conns"], dtype=np.int64)
-            ctx.build_laplacian(conns, g, self.Np)
+            ctx.build_laplacian(self._device_conns(ctx), g, self.Np)
             self._cache_key = key
         nsrc = len(self._sources())
         f, nnz = ctx.apply_bcs(self["pore.bc.value"], self["pore.bc.rate"],
@@ -244,8 +265,6 @@ class Transport(dict):
             raise TypeError("openpnm_b200 algorithms need a B200PCG solver "
                             "(there is no CPU path)")
         self._validate_settings()
-        if self.settings["validate_topology"]:
-            self._validate_topology_health()
         x0 = np.zeros(self.Np) if x0 is None else np.array(x0, dtype=np.float64)
         if not np.isfinite(x0).all():
             raise Exception("x0 contains inf/nan values")
@@ -255,6 +274,8 @@ class Transport(dict):
         ctx = solver.ctx
         self._ctx = ctx
         ctx.set_format(solver._fmt_code())
+        if self.settings["validate_topology"]:
+            self._validate_topology_health(ctx)
         try:
             self._assemble(ctx)
             ctx.clear_sources()

@@ -103,6 +103,18 @@ class Context:
         self.row_begin = int(row_begin)
         return nnz.value
 
+    def check_topology(self, conns, Np, bc_value=None, bc_rate=None):
+        """(number of clusters, number of clusters without any BC pore)"""
+        torch = _torch()
+        conns = self.to_device(conns, torch.int64)
+        bv = self.to_device(bc_value, torch.float64) if bc_value is not None else None
+        br = self.to_device(bc_rate, torch.float64) if bc_rate is not None else None
+        nc, nb = C.c_int64(), C.c_int64()
+        self._ck(self.lib.b200_check_topology(self._h, self._p(conns), int(conns.numel() // 2),
+                                              int(Np), self._p(bv), self._p(br), C.byref(nc),
+                                              C.byref(nb)))
+        return nc.value, nb.value
+
     def apply_bcs(self, bc_value=None, bc_rate=None, keep_zero_diag=False):
         torch = _torch()
         bv = self.to_device(bc_value, torch.float64) if bc_value is not None else None

@@ -372,3 +372,41 @@ def test_large_properties_cubic_128(b2):
     ctx.apply_bcs(2 * bcv, None)
     ip2, ix2, dt2 = ctx.export_csr(1)
     assert bool((ip1 == ip2).all()) and bool((ix1 == ix2).all()) and bool((dt1 == dt2).all())
+
+
+def test_topology_check_on_device(b2):
+    """GenericTransportTest.py:51-61: clusters without a BC pore raise; clusters
+    that carry their own BC are fine; counts agree with scipy."""
+    import scipy.sparse as sprs
+    from scipy.sparse import csgraph
+    rng = np.random.default_rng(4)
+    Np = 5000
+    conns = np.sort(rng.integers(0, Np, size=(4200, 2)), axis=1)     # sparse: many clusters
+    conns = conns[conns[:, 0] != conns[:, 1]]
+    am = sprs.coo_matrix((np.ones(len(conns)), (conns[:, 0], conns[:, 1])), shape=(Np, Np))
+    ncomp, labels = csgraph.connected_components(am, directed=False)
+    bcv = np.full(Np, np.nan)
+    bcv[rng.choice(Np, 300, replace=False)] = 1.0
+    bcr = np.full(Np, np.nan)
+    bcr[rng.choice(Np, 100, replace=False)] = 0.5
+    touched = np.zeros(ncomp, dtype=bool)
+    touched[labels[np.isfinite(bcv) | np.isfinite(bcr)]] = True
+    ctx = b2.B200PCG().ctx
+    nc, nbad = ctx.check_topology(conns, Np, bcv, bcr)
+    assert nc == ncomp and nbad == int((~touched).sum())
+    assert ctx.check_topology(conns, Np, np.ones(Np), None) == (ncomp, 0)
+    # through the algorithm: same exception text as the reference
+    pn = b2.Network(conns=[[0, 1], [1, 2], [3, 4]], Np=5)
+    ph = b2.Phase(pn)
+    ph["throat.g"] = 1.0
+    alg = b2.Transport(network=pn, phase=ph, quantity="pore.x", conductance="throat.g")
+    alg.set_value_BC(pores=[0], values=1.0)
+    alg.set_value_BC(pores=[2], values=0.0)
+    with pytest.raises(Exception, match="clustered"):
+        alg.run()
+    alg.set_value_BC(pores=[3], values=0.5)
+    alg.run(solver=b2.B200PCG(tol=1e-14))
+    np.testing.assert_allclose(alg.x, [1.0, 0.5, 0.0, 0.5, 0.5], atol=1e-12)
+    # a big lattice is one cluster
+    pn = b2.Cubic([60, 60, 60], coords=False)
+    assert ctx.check_topology(pn.conns, pn.Np, None, None) == (1, 1)
