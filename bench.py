@@ -287,6 +287,14 @@ def gpu_arm(args):
         fmt_spmv = 12 * (nnz_loc - n_loc) + 4 * n_loc + 24 * n_loc
     fmt_iter = fmt_spmv + 56 * n_loc          # K_BC: read x,r,p,Ap, write x,r,p
     peak, peak_src = peaks()
+    traffic = None
+    try:     # DRAM bytes per launch from the committed ncu capture of this very configuration
+        if world == 1 and n == 400 and fmt_code == 2:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tk = json.load(f)["cubic400_1gpu_dia"]["k_dia_spmv_dot"]
+            traffic = tk["dram_read_bytes"] + tk["dram_write_bytes"]
+    except Exception:
+        traffic = None
     ms_iter = float(np.mean(t_solve_ms)) / max(cg_iters, 1)
 
     # ---- e2e through the public API with HOST buffers: every step copies its
@@ -378,7 +386,7 @@ def gpu_arm(args):
             "roofline": {"bound": "hbm", "kernel": "K_A SpMV + 3 dots (k_dia_spmv_dot / "
                          "k_csr_stream_spmv_dot)", "achieved": b_spmv / (t_ka * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s",
-                         "frac": b_spmv / (t_ka * 1e-3) / 1e9 / peak, "traffic": None,
+                         "frac": b_spmv / (t_ka * 1e-3) / 1e9 / peak, "traffic": traffic,
                          "peak_source": peak_src, "ms": t_ka,
                          "algorithmic_bytes": int(b_spmv), "format_bytes": int(fmt_spmv),
                          "frac_format_bytes": fmt_spmv / (t_ka * 1e-3) / 1e9 / peak},
