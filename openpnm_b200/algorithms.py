@@ -294,10 +294,10 @@ class Transport(dict):
                 raise Exception("A or b contains inf/nan values") from e
             raise
         self._x_dev = x_dev
-        x = x_dev.cpu().numpy()
-        self.x = x
+        x = self._download(ctx, x_dev)
         q = self.settings["quantity"]
-        self.soln[q] = SteadyStateSolution(x.copy())
+        dict.__setitem__(self, q, x)
+        self.soln[q] = SteadyStateSolution(x)      # a view, as in _solution.py:17-20
         self.soln.is_converged = bool(conv)
         self.soln.num_iter = int(num_iter)
         self.soln.cg_iters = int(cg_iters)
@@ -310,6 +310,19 @@ class Transport(dict):
 
     def _post_run(self, x):
         pass
+
+    def _download(self, ctx, x_dev):
+        """Device -> host through a page-locked staging buffer (kept per size)."""
+        import torch
+        n = int(x_dev.numel())
+        stage = getattr(self, "_x_stage", None)
+        if stage is None or stage.numel() != n:
+            stage = torch.empty(n, dtype=torch.float64, pin_memory=True)
+            self._x_stage = stage
+        with torch.cuda.stream(ctx.stream):
+            stage.copy_(x_dev, non_blocking=True)
+        ctx.synchronize()
+        return stage.numpy().copy()
 
     @property
     def A(self):

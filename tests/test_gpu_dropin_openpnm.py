@@ -1,0 +1,125 @@
+"""GPU + the REAL reference: `openpnm` (unmodified, from /root/reference or the
+offline install under baseline/_ref) driven with the B200 solver and with the
+B200 algorithms.  Skipped when the reference is not importable."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_shim  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def op():
+    if ref_shim.find_reference() is None:
+        pytest.skip("reference OpenPNM not available")
+    mod = ref_shim.import_reference()
+    yield mod
+    mod.Workspace().clear()
+
+
+def hetero(nt, seed=0):
+    return 10.0 ** np.random.default_rng(seed).uniform(-15, -12, nt)
+
+
+def test_reference_stokesflow_with_b200pcg(op, b2):
+    """alg.run(solver=B200PCG()) on the reference's own StokesFlow, against the
+    reference's own ScipySpsolve answer (north star: x and rate within 1e-8)."""
+    pn = op.network.Cubic(shape=[15, 15, 15], spacing=1e-4)
+    ph = op.phase.Phase(network=pn)
+    ph["throat.hydraulic_conductance"] = hetero(pn.Nt)
+    sf = op.algorithms.StokesFlow(network=pn, phase=ph)
+    sf.set_value_BC(pores=pn.pores("left"), values=2e5)
+    sf.set_value_BC(pores=pn.pores("right"), values=1e5)
+    sf.run(solver=op.solvers.ScipySpsolve())
+    x_ref = np.array(sf.x)
+    q_ref = sf.rate(pores=pn.pores("left"))[0]
+    solver = b2.B200PCG(tol=1e-13)
+    sf.run(solver=solver)                       # _transport.py:213 calls solver.solve(A=, b=, x0=)
+    assert sf.soln.is_converged and sf.soln.num_iter == 1
+    assert np.max(np.abs(sf.x - x_ref) / np.abs(x_ref)) < 1e-8
+    assert abs(sf.rate(pores=pn.pores("left"))[0] - q_ref) <= 1e-8 * abs(q_ref)
+    assert solver.info["fmt"] == "dia" and solver.info["exit_code"] == 0
+
+
+def test_default_solver_registration(op, b2):
+    """op.Workspace().settings.default_solver = 'B200PCG' (utils/_workspace.py:44-56)."""
+    b2.register_with_openpnm(op)
+    ws = op.Workspace()
+    old = ws.settings.default_solver
+    try:
+        ws.settings.default_solver = "B200PCG"
+        pn = op.network.Cubic(shape=[9, 9, 9])
+        ph = op.phase.Phase(network=pn)
+        ph["throat.diffusive_conductance"] = 1.0
+        fd = op.algorithms.FickianDiffusion(network=pn, phase=ph)
+        fd.set_value_BC(pores=pn.pores("top"), values=1)
+        fd.set_value_BC(pores=pn.pores("bottom"), values=0)
+        fd.run()                                  # no solver argument: getattr(solvers, name)()
+        np.testing.assert_allclose(fd.rate(pores=pn.pores("top"))[0], 10.125, rtol=1e-6)
+    finally:
+        ws.settings.default_solver = old
+
+
+def test_reference_reactive_loop_with_b200pcg(op, b2):
+    """The reference's own Picard loop (_reactive_transport.py:150-213) calling
+    the B200 solver once per outer iteration: ReactiveTransportTest.py:69-77."""
+    from openpnm.models.physics import source_terms
+    pn = op.network.Cubic(shape=[4, 4, 4])
+    ph = op.phase.Phase(network=pn)
+    ph["throat.diffusive_conductance"] = 1e-15
+    ph["pore.A"] = -1e-15
+    ph["pore.k"] = 2
+    ph.add_model(propname="pore.reaction", model=source_terms.standard_kinetics,
+                 prefactor="pore.A", exponent="pore.k", X="pore.concentration",
+                 regen_mode="deferred")
+    alg = op.algorithms.ReactiveTransport(network=pn, phase=ph)
+    alg.settings._update({"conductance": "throat.diffusive_conductance",
+                          "quantity": "pore.concentration"})
+    alg.set_source(pores=pn.pores("bottom"), propname="pore.reaction")
+    alg.set_value_BC(pores=pn.pores("top"), values=1.0)
+    alg.run(solver=b2.B200PCG(tol=1e-13))
+    np.testing.assert_allclose(alg["pore.concentration"].mean(), 0.7171292729553325, rtol=1e-8)
+    assert alg.soln.num_iter == 6 and alg.soln.is_converged
+
+
+def test_b200_algorithms_accept_reference_objects(op, b2):
+    """openpnm_b200.ReactiveTransport on real OpenPNM network/phase objects (device
+    assembly + device Picard loop) against the reference's own run."""
+    from openpnm.models.physics import source_terms
+    pn = op.network.Cubic(shape=[12, 12, 12], spacing=1e-4)
+    ph = op.phase.Phase(network=pn)
+    ph["throat.diffusive_conductance"] = hetero(pn.Nt, 3)
+    ph["pore.A1"] = -1e-13
+    ph["pore.A2"] = 2.0
+    ph["pore.A3"] = 0.0
+    ph.add_model(propname="pore.rxn", model=source_terms.power_law, A1="pore.A1", A2="pore.A2",
+                 A3="pore.A3", X="pore.concentration", regen_mode="deferred")
+    src = np.setdiff1d(pn.Ps, pn.pores("left"))
+    ref = op.algorithms.ReactiveTransport(network=pn, phase=ph)
+    ref.settings._update({"conductance": "throat.diffusive_conductance",
+                          "quantity": "pore.concentration"})
+    ref.set_source(pores=src, propname="pore.rxn")
+    ref.set_value_BC(pores=pn.pores("left"), values=1.0)
+    ref.run(solver=op.solvers.ScipySpsolve())
+    c_ref = np.array(ref["pore.concentration"])
+    q_ref = ref.rate(pores=pn.pores("left"))[0]
+    A_ref = ref.A.tocsr()
+    A_ref.sort_indices()
+
+    alg = b2.ReactiveTransport(network=pn, phase=ph)
+    alg.settings._update({"conductance": "throat.diffusive_conductance",
+                          "quantity": "pore.concentration"})
+    alg.set_source(pores=src, propname="pore.rxn")
+    alg.set_value_BC(pores=pn.pores("left"), values=1.0)
+    alg.run(solver=b2.B200PCG(tol=1e-13))
+    assert alg.soln.num_iter == ref.soln.num_iter and alg.soln.is_converged
+    assert np.max(np.abs(alg.x - c_ref)) <= 1e-8 * np.max(np.abs(c_ref))
+    assert abs(alg.rate(pores=pn.pores("left"))[0] - q_ref) <= 1e-8 * abs(q_ref)
+    A = alg.A
+    assert np.array_equal(A.indptr, A_ref.indptr) and np.array_equal(A.indices, A_ref.indices)
+    np.testing.assert_allclose(A.data, A_ref.data, rtol=1e-7, atol=0)
