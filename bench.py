@@ -118,28 +118,83 @@ def cpu_solve_sample(n, rtol=RTOL):
                 t_solve=t3 - t2, t_rate=t4 - t3, t_step=t4 - t1, rate=q)
 
 
+def reference_openpnm_sample(n, rtol=RTOL):
+    """The REAL reference (unmodified OpenPNM from baseline/_ref or /root/reference,
+    imported through tests/ref_shim.py): `StokesFlow.run(solver=ScipyCG(tol))` + `rate()`
+    on a Cubic n^3 sample -- its own assembly (x3), topology check and SciPy CG.
+    Returns None when the reference cannot be imported."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import ref_shim
+        op = ref_shim.import_reference()
+    except Exception:
+        op = None
+    if op is None:
+        return None
+    import logging
+    logging.disable(logging.CRITICAL)
+    pn = op.network.Cubic(shape=[n, n, n], spacing=1e-4)
+    ph = op.phase.Phase(network=pn)
+    ph["throat.hydraulic_conductance"] = conductance(pn.Nt)
+    sf = op.algorithms.StokesFlow(network=pn, phase=ph)
+    sf.set_value_BC(pores=pn.pores("left"), values=P_IN)
+    sf.set_value_BC(pores=pn.pores("right"), values=P_OUT)
+    its = [0]
+
+    class CountingCG(op.solvers.ScipyCG):
+        def solve(self, A, b, **kw):
+            def cb(xk):
+                its[0] += 1
+            return super().solve(A, b, callback=cb, **kw)
+
+    t0 = time.perf_counter()
+    sf.run(solver=CountingCG(tol=rtol))
+    q = sf.rate(pores=pn.pores("left"))[0]
+    dt = time.perf_counter() - t0
+    out = dict(Np=pn.Np, iters=its[0], t_step=dt, rate=float(q),
+               converged=bool(sf.soln.is_converged))
+    op.Workspace().clear()
+    return out
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n = args.cpu_size
     try:
         import threadpoolctl
         threads = max(d.get("num_threads", 1) for d in threadpoolctl.threadpool_info()) or 1
     except Exception:
         threads = 1
-    for _ in range(args.warmup):
-        cpu_solve_sample(min(n, 40))
-    t, its, Np = [], 0, 0
-    for _ in range(args.steps):
-        r = cpu_solve_sample(n)
-        t.append(r["t_step"])
-        its, Np = r["iters"], r["Np"]
+    n = args.ref_size
+    real = reference_openpnm_sample(min(n, 24))        # also the import probe / warm-up
+    if real is not None:
+        for _ in range(max(args.warmup - 1, 0)):
+            reference_openpnm_sample(min(n, 24))
+        t, its, Np = [], 0, 0
+        for _ in range(args.steps):
+            r = reference_openpnm_sample(n)
+            t.append(r["t_step"])
+            its, Np = r["iters"], r["Np"]
+        kind = "reference"
+        sample = (f"unmodified OpenPNM StokesFlow.run(solver=ScipyCG(tol={RTOL:g})) + rate() on "
+                  f"Cubic {n}^3 (same g distribution/BCs as the GPU arm's Cubic {args.size}^3): "
+                  f"its own topology check, 3 assemblies and SciPy's serial CG, {its} iterations")
+    else:
+        n = args.cpu_size
+        for _ in range(args.warmup):
+            cpu_solve_sample(min(n, 40))
+        t, its, Np = [], 0, 0
+        for _ in range(args.steps):
+            r = cpu_solve_sample(n)
+            t.append(r["t_step"])
+            its, Np = r["iters"], r["Np"]
+        kind = "port"
+        sample = (f"Cubic {n}^3 StokesFlow (same g distribution/BCs/rtol as the GPU arm's Cubic "
+                  f"{args.size}^3): numpy assembly as the reference + SciPy CSR SpMV Jacobi-PCG, "
+                  f"{its} iterations; SciPy's SpMV and CG are serial")
     ms = 1e3 * float(np.mean(t))
     val = Np * its / (ms * 1e-3)
-    sample = (f"Cubic {n}^3 StokesFlow (same g distribution/BCs/rtol as the GPU arm's Cubic "
-              f"{args.size}^3): numpy assembly as the reference + SciPy CSR SpMV Jacobi-PCG, "
-              f"{its} iterations; SciPy's SpMV and CG are serial")
     line = {
         "impl": "reference", "metric": "stokesflow_dof_iter_per_s", "value": val,
         "unit": "DOF*iter/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -147,7 +202,7 @@ def reference_arm(args):
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.size, None, None, None),
         "time_to_solve_s": ms * 1e-3,
-        "cpu_baseline": {"value": val, "unit": "DOF*iter/s", "cores": 1, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "DOF*iter/s", "cores": 1, "kind": kind,
                          "blas_threads": threads, "sample": sample},
         "e2e": {"value": val, "unit": "DOF*iter/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -358,12 +413,20 @@ def gpu_arm(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = cpu_solve_sample(args.cpu_size)
-        cpu = {"value": r["Np"] * r["iters"] / r["t_step"], "unit": "DOF*iter/s", "cores": 1,
-               "kind": "port",
-               "sample": f"Cubic {args.cpu_size}^3 same distribution/BCs/rtol, {r['iters']} "
-                         f"iterations, {r['t_step']:.1f} s (assembly {r['t_assemble']:.1f} s); "
-                         f"numpy assembly + SciPy CSR SpMV Jacobi-PCG, serial"}
+        r = reference_openpnm_sample(args.ref_size)
+        if r is not None:
+            cpu = {"value": r["Np"] * r["iters"] / r["t_step"], "unit": "DOF*iter/s", "cores": 1,
+                   "kind": "reference",
+                   "sample": f"unmodified OpenPNM StokesFlow.run(solver=ScipyCG(tol={RTOL:g})) + "
+                             f"rate() on Cubic {args.ref_size}^3, same distribution/BCs: "
+                             f"{r['iters']} iterations, {r['t_step']:.1f} s; SciPy CG is serial"}
+        else:
+            r = cpu_solve_sample(args.cpu_size)
+            cpu = {"value": r["Np"] * r["iters"] / r["t_step"], "unit": "DOF*iter/s", "cores": 1,
+                   "kind": "port",
+                   "sample": f"Cubic {args.cpu_size}^3 same distribution/BCs/rtol, {r['iters']} "
+                             f"iterations, {r['t_step']:.1f} s (assembly {r['t_assemble']:.1f} s); "
+                             f"numpy assembly + SciPy CSR SpMV Jacobi-PCG, serial"}
 
     if rank == 0:
         line = {
@@ -416,6 +479,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=int(os.environ.get("B200_BENCH_SIZE", "400")))
     ap.add_argument("--cpu-size", type=int, default=100)
+    ap.add_argument("--ref-size", type=int, default=64)
     ap.add_argument("--fmt", default="auto", choices=["auto", "csr", "dia"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-p2p", action="store_true")
