@@ -265,10 +265,11 @@ class Transport(dict):
             raise TypeError("openpnm_b200 algorithms need a B200PCG solver "
                             "(there is no CPU path)")
         self._validate_settings()
+        x0_given = x0 is not None
         x0 = np.zeros(self.Np) if x0 is None else np.array(x0, dtype=np.float64)
-        if not np.isfinite(x0).all():
+        if x0_given and not np.isfinite(x0).all():
             raise Exception("x0 contains inf/nan values")
-        self["pore.initial_guess"] = x0
+        dict.__setitem__(self, "pore.initial_guess", x0)
         self.soln = SolutionContainer()
         self.soln.is_converged = False
         ctx = solver.ctx
@@ -284,7 +285,7 @@ class Transport(dict):
             s = self.settings
             cg_rtol = s["cg_rtol"] if s.get("cg_rtol") else solver.tol
             x_dev, num_iter, conv, cg_iters, info = ctx.picard(
-                x0=x0 if np.any(x0) else None,
+                x0=x0 if x0_given else None,
                 relaxation=s.get("relaxation_factor", 1.0),
                 newton_maxiter=s.get("newton_maxiter", 5000),
                 f_rtol=s.get("f_rtol", 1e-6), x_rtol=s.get("x_rtol", 1e-6),
@@ -445,7 +446,10 @@ class ReactiveTransport(Transport):
 
     def _post_run(self, x):
         """Leave S1 / S2 / rate of each source on the phase at the converged x,
-        as `regenerate_models` does in the reference (_algorithm.py:89-91)."""
+        as `regenerate_models` does in the reference (_algorithm.py:89-91); like
+        there, nothing is written when no property depends on the quantity."""
+        if not self["pore.source"]:
+            return
         try:
             self._phase[self.settings["quantity"]] = x
         except Exception:
