@@ -358,7 +358,9 @@ __global__ void k_rowstart(const int* __restrict__ optr, int64_t n, int64_t Q, i
   rowstart[q] = (int)lo;
 }
 
+#ifndef CSR_Q
 #define CSR_Q 2048          // work units (entries + rows) per CTA
+#endif
 #define CSR_MAXROW 4096     // longest row the streaming kernel accepts
 
 static int prepare_operator(b200_ctx* ctx) {
@@ -570,7 +572,20 @@ __global__ void __launch_bounds__(PCG_T) k_csr_stream_spmv_dot(
   for (int q = blockIdx.x; q < nblocks; q += gridDim.x) {
     const int r0 = rowstart[q], r1 = rowstart[q + 1];
     const int e0 = optr[r0], e1 = optr[r1];
-    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) prod[e - e0] = ovals[e] * p[ocols[e]];
+    int e = e0 + threadIdx.x;
+    // four independent (val, col, gather) chains in flight per thread
+    for (; e + 3 * PCG_T < e1; e += 4 * PCG_T) {
+      const int c0 = ocols[e], c1 = ocols[e + PCG_T], c2 = ocols[e + 2 * PCG_T],
+                c3 = ocols[e + 3 * PCG_T];
+      const double v0 = ovals[e], v1 = ovals[e + PCG_T], v2 = ovals[e + 2 * PCG_T],
+                   v3 = ovals[e + 3 * PCG_T];
+      const double x0 = p[c0], x1 = p[c1], x2 = p[c2], x3 = p[c3];
+      prod[e - e0] = v0 * x0;
+      prod[e + PCG_T - e0] = v1 * x1;
+      prod[e + 2 * PCG_T - e0] = v2 * x2;
+      prod[e + 3 * PCG_T - e0] = v3 * x3;
+    }
+    for (; e < e1; e += PCG_T) prod[e - e0] = ovals[e] * p[ocols[e]];
     __syncthreads();
     for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
       const double pi = p[r];

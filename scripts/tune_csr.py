@@ -41,18 +41,16 @@ def run(name, conns, Np, bcv, block):
 
 
 if __name__ == "__main__":
-    n = 160
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     pn = b2.Cubic([n, n, n], coords=False)
     bcv = np.full(pn.Np, np.nan)
     bcv[pn.pores("left")] = 1.0
     bcv[pn.pores("right")] = 0.0
-    for block in (True, False):
-        run(f"cubic{n}", pn.conns, pn.Np, bcv, block)
+    run(f"cubic{n}", pn.conns, pn.Np, bcv, True)
     t0 = time.time()
     pts, conns = delaunay(int(sys.argv[1]) if len(sys.argv) > 1 else 400000)
     print(f"delaunay built in {time.time()-t0:.1f}s, band {bdist.bandwidth(conns)}", flush=True)
     bcv = np.full(len(pts), np.nan)
     bcv[pts[:, 0] < 0.01] = 1.0
     bcv[pts[:, 0] > 0.99] = 0.0
-    for block in (True, False):
-        run("delaunay", conns, len(pts), bcv, block)
+    run("delaunay", conns, len(pts), bcv, True)
