@@ -205,8 +205,15 @@ class SlabSolver:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             return False
+        def all_ok(flag):
+            t = torch.tensor([1 if flag else 0], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return bool(int(t.item()))
+
         buf = (C.c_ubyte * 128)()
-        ctx._ck(ctx.lib.b200_p2p_export(ctx._h, C.cast(buf, C.c_void_p)))
+        ok = ctx.lib.b200_p2p_export(ctx._h, C.cast(buf, C.c_void_p)) == 0
+        if not all_ok(ok):            # every rank takes the same decision
+            return False
         mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
         allh = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(allh, mine)
@@ -216,9 +223,11 @@ class SlabSolver:
         raw = b"".join(bytes(t.cpu().tolist()) for t in allh)
         hbuf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
         rbuf = (C.c_int64 * self.world)(*[int(t.item()) for t in allr])
-        ctx._ck(ctx.lib.b200_p2p_attach(ctx._h, C.cast(hbuf, C.c_void_p),
-                                        C.cast(rbuf, C.c_void_p)))
-        dist.barrier()
+        ok = ctx.lib.b200_p2p_attach(ctx._h, C.cast(hbuf, C.c_void_p),
+                                     C.cast(rbuf, C.c_void_p)) == 0
+        if not all_ok(ok):            # e.g. IPC not permitted: stay on the NCCL back end
+            self.disable_p2p()
+            return False
         return True
 
     def disable_p2p(self):
