@@ -632,40 +632,84 @@ __global__ void k_bc_count(const int* __restrict__ indptr, const int* __restrict
   if (bad) flags[FLAG_NONFINITE] = 1;
 }
 
-__global__ void k_bc_emit(const int* __restrict__ indptr, const int* __restrict__ indices,
-                          const double* __restrict__ data, int64_t n, int64_t rb,
-                          const double* __restrict__ bcv, double f, int keep_zero_diag,
-                          const int* __restrict__ optr, int* __restrict__ oidx,
-                          double* __restrict__ odat, double* __restrict__ odiag,
-                          int* __restrict__ odiagpos, int* __restrict__ flags) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+// Row pass 2, warp-cooperative: a warp takes 32 consecutive rows, streams their
+// entries coalesced (32 lanes = 32 consecutive entries), finds each entry's row
+// by a 5-step binary search over the 32 row pointers held one per lane
+// (shuffles), evaluates the keep rule and compacts order-preservingly with
+// ballot/popc -- the output segment of the chunk is contiguous, so the writes
+// are coalesced as well.  Integer work only; same result as a per-row walk.
+__global__ void __launch_bounds__(256) k_bc_emit(const int* __restrict__ indptr,
+                                                 const int* __restrict__ indices,
+                                                 const double* __restrict__ data, int64_t n,
+                                                 int64_t rb, const double* __restrict__ bcv,
+                                                 double f, int keep_zero_diag,
+                                                 const int* __restrict__ optr,
+                                                 int* __restrict__ oidx, double* __restrict__ odat,
+                                                 double* __restrict__ odiag,
+                                                 int* __restrict__ odiagpos,
+                                                 int* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t nchunks = (n + 31) >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
   bool bad = false;
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
-    const int64_t gi = r + rb;
-    const double vi = bcv ? bcv[gi] : nan("");
-    int o = optr[r];
-    double d = 0.0;
-    int dp = -1;
-    if (isfinite(vi)) {
-      if (f != 0.0 || keep_zero_diag) { oidx[o] = (int)gi; odat[o] = f; dp = o; }
-      d = f;
-    } else {
-      for (int e = indptr[r]; e < indptr[r + 1]; ++e) {
-        const int j = indices[e];
-        const double a = data[e];
-        const double vj = bcv ? bcv[j] : nan("");
-        if (isfinite(vj)) continue;
-        const bool isdiag = ((int64_t)j == gi);
-        if (a != 0.0 || (keep_zero_diag && isdiag)) {
-          if (!isfinite(a)) bad = true;
-          oidx[o] = j; odat[o] = a;
-          if (isdiag) { d = a; dp = o; }
-          ++o;
+  for (int64_t ch = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ch < nchunks;
+       ch += nwarps) {
+    const int64_t r0 = ch << 5;
+    const int64_t r = r0 + lane;
+    const int my_ptr = indptr[r < n ? r : n];
+    const int e_begin = __shfl_sync(0xffffffffu, my_ptr, 0);
+    const int64_t rlast = r0 + 32 < n ? r0 + 32 : n;
+    const int e_end = indptr[rlast];
+    int out = optr[r0];
+    bool row_bc = false;
+    if (r < n) {
+      const double vi = bcv ? bcv[r + rb] : nan("");
+      row_bc = isfinite(vi);
+      odiag[r] = row_bc ? f : 0.0;      // overwritten below when the diagonal entry survives
+      odiagpos[r] = -1;
+    }
+    const unsigned bc_mask = __ballot_sync(0xffffffffu, row_bc);
+    __syncwarp();
+    for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+      const int e = e0 + lane;
+      const bool valid = e < e_end;
+      int j = 0;
+      double a = 0.0;
+      if (valid) { j = indices[e]; a = data[e]; }
+      // row of e: the last lane whose row pointer is <= e
+      int lo = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int cand = lo + step;
+        const int pc = __shfl_sync(0xffffffffu, my_ptr, cand & 31);
+        if (cand < 32 && pc <= e) lo = cand;
+      }
+      const int64_t row = r0 + lo;
+      const bool rbc = (bc_mask >> lo) & 1u;
+      const bool isdiag = ((int64_t)j == row + rb);
+      bool keep = false;
+      double val = a;
+      if (valid) {
+        if (rbc) {
+          keep = isdiag && (f != 0.0 || keep_zero_diag);
+          val = f;
+        } else {
+          const double vj = bcv ? bcv[j] : nan("");
+          keep = !isfinite(vj) && (a != 0.0 || (keep_zero_diag && isdiag));
         }
       }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int pos = out + __popc(m & lt_mask);
+        if (!isfinite(val)) bad = true;
+        oidx[pos] = j;
+        odat[pos] = val;
+        if (isdiag) { odiag[row] = val; odiagpos[row] = pos; }
+      }
+      out += __popc(m);
     }
-    odiag[r] = d;
-    odiagpos[r] = dp;
+    __syncwarp();
   }
   if (bad) flags[FLAG_NONFINITE] = 1;
 }
@@ -696,7 +740,7 @@ extern "C" int b200_apply_bcs(b200_ctx* ctx, const double* bc_value, const doubl
   int64_t total = 0;
   RET(b200_scan_exclusive_i32(ctx, cnt, ctx->sys_indptr.as<int>(), n, &total));
   RET(alloc_system(ctx, n, total));
-  LAUNCH(ctx, k_bc_emit, grid_for(n, 128), 128, 0, ctx->pure_indptr.as<int>(),
+  LAUNCH(ctx, k_bc_emit, grid_for(n, 256 / 32), 256, 0, ctx->pure_indptr.as<int>(),
          ctx->pure_indices.as<int>(), ctx->pure_data.as<double>(), n, ctx->row_begin, bc_value, f,
          keep_zero_diag, ctx->sys_indptr.as<int>(), ctx->sys_indices.as<int>(),
          ctx->sys_data.as<double>(), ctx->sys_diag.as<double>(), ctx->sys_diagpos.as<int>(),
