@@ -147,11 +147,17 @@ class Cubic(Network):
             dict.__setitem__(self, "pore.coords", c)
 
     def _face(self, axis, last):
+        """Sorted pore indices of one face, from index arithmetic (no Np-long temporaries)."""
         nx, ny, nz = self.shape
-        idx = np.arange(self._Np, dtype=np.int64).reshape(nx, ny, nz)
-        sl = [slice(None)] * 3
-        sl[axis] = -1 if last else 0
-        return np.sort(idx[tuple(sl)].ravel())
+        ax, ay, az = (np.arange(m, dtype=np.int64) for m in (nx, ny, nz))
+        if axis == 0:
+            x = nx - 1 if last else 0
+            return x * ny * nz + np.arange(ny * nz, dtype=np.int64)
+        if axis == 1:
+            y = ny - 1 if last else 0
+            return (ax[:, None] * (ny * nz) + y * nz + az[None, :]).ravel()
+        z = nz - 1 if last else 0
+        return ((ax[:, None] * ny + ay[None, :]) * nz + z).ravel()
 
     _FACES = {"left": (0, False), "right": (0, True), "front": (1, False), "back": (1, True),
               "bottom": (2, False), "top": (2, True), "xmin": (0, False), "xmax": (0, True),
