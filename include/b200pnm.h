@@ -163,6 +163,24 @@ int b200_picard(b200_ctx* ctx, const double* x0, double relaxation,
                 int64_t* num_iter, int* converged, int64_t* cg_iters_total,
                 int* last_info);
 
+/* ------------------------------------------------ transient (explicit RK45)
+ * Replaces TransientReactiveTransport.run + _build_rhs
+ * (openpnm/algorithms/_transient_reactive_transport.py:51-123) with
+ * integrators.ScipyRK45 (openpnm/integrators/_scipy.py:18-56):
+ *   dy/dt = (-A y + b) / V,  A, b = system after BCs with the registered
+ * sources linearised at y, integrated from t0 to t1 by SciPy's RK45 scheme
+ * (Dormand-Prince 5(4), same step controller and dense output).  x0 must
+ * already carry the BC values on the BC pores.  saveat_h (host, ascending,
+ * within [t0, t1]) are the output times (t_eval); nsave = 0 stores every
+ * accepted step like t_eval=None.  out: device, `capacity` rows of n;
+ * times_h: host, `capacity` doubles.  status: 0 finished, -1 step size too
+ * small, -2 capacity exhausted.                                             */
+int b200_transient_rk45(b200_ctx* ctx, const double* x0, const double* volume,
+                        double t0, double t1, double rtol, double atol,
+                        const double* saveat_h, int64_t nsave, int64_t capacity,
+                        double* out, double* times_h, int64_t* nout,
+                        int64_t* nsteps, int64_t* nfev, int* status);
+
 /* ---------------------------------------------------------------- K6: rate
  * Replaces Transport.rate (_transport.py:259-330).  Pores: net rate leaving
  * each pore = (L_pure x)[pore]; out has k entries (mode 'single') and the

@@ -13,9 +13,11 @@ or, with assembly / boundary conditions / Picard loop on the device as well:
 Only the hot path lives here; everything needs a CUDA device
 and the in-tree libb200pnm.so -- there is no CPU fallback.
 """
-from . import _lib, algorithms, network, solvers
+from . import _lib, algorithms, integrators, network, solvers
 from .algorithms import (FickianDiffusion, FourierConduction, OhmicConduction,
-                         ReactiveTransport, StokesFlow, Transport)
+                         ReactiveTransport, StokesFlow, TransientFickianDiffusion,
+                         TransientReactiveTransport, Transport)
+from .integrators import B200RK45
 from .network import Cubic, Network, Phase
 from .solvers import B200PCG
 

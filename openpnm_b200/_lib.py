@@ -69,6 +69,8 @@ SIGNATURES = {
     "b200_add_source": (C.c_int, [_p, C.c_int, _p, _p, _p, _p]),
     "b200_picard": (C.c_int, [_p, _p, _dbl, _i64, _dbl, _dbl, _dbl, _i64, _p, _pi64, _pint,
                               _pi64, _pint]),
+    "b200_transient_rk45": (C.c_int, [_p, _p, _p, _dbl, _dbl, _dbl, _dbl, _p, _i64, _i64, _p, _p,
+                                      _pi64, _pi64, _pi64, _pint]),
     "b200_rate_pores": (C.c_int, [_p, _p, _p, _i64, _p]),
     "b200_rate_throats": (C.c_int, [_p, _p, _p, _p, _p, _i64, _p]),
     "b200_get_stats": (C.c_int, [_p, C.POINTER(Stats)]),

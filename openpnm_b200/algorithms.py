@@ -23,7 +23,9 @@ from . import _lib
 from .solvers import B200PCG
 
 __all__ = ["Transport", "ReactiveTransport", "StokesFlow", "FickianDiffusion",
-           "OhmicConduction", "FourierConduction", "SolutionContainer", "SteadyStateSolution"]
+           "OhmicConduction", "FourierConduction", "SolutionContainer", "SteadyStateSolution",
+           "TransientReactiveTransport", "TransientFickianDiffusion",
+           "TransientOhmicConduction", "TransientFourierConduction", "TransientSolution"]
 
 logger = logging.getLogger(__name__)
 
@@ -45,6 +47,32 @@ class SteadyStateSolution(np.ndarray):
 
     def __new__(cls, x):
         return np.asarray(x).view(cls)
+
+
+class TransientSolution(np.ndarray):
+    """openpnm/algorithms/_solution.py:23-84: the (Np, Nt) array of stored states
+    with the stored times in `.t`; calling it interpolates linearly in time."""
+
+    def __new__(cls, t, y):
+        obj = np.asarray(y).view(cls)
+        obj._x = np.asarray(t)
+        return obj
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._x = getattr(obj, "_x", None)
+
+    @property
+    def t(self):
+        return self._x
+
+    def interpolate(self, t):
+        from scipy.interpolate import interp1d
+        if not hasattr(self, "_interpolant") or self._interpolant is None:
+            self._interpolant = interp1d(self._x, np.asarray(self), bounds_error=True)
+        return self._interpolant(t)
+
+    __call__ = interpolate
 
 
 class Settings(dict):
@@ -481,6 +509,99 @@ class ReactiveTransport(Transport):
                 self._phase[f"pore.{item}.rate"] = r
             except Exception:
                 pass
+
+
+class TransientReactiveTransport(ReactiveTransport):
+    """dy/dt = (-A y + b) / V integrated on the device (reference:
+    TransientReactiveTransport, _transient_reactive_transport.py:30-123)."""
+
+    def __init__(self, network, phase, name="trans_react_?", **kwargs):
+        super().__init__(network=network, phase=phase, name=name, **kwargs)
+        self.settings.setdefault("pore_volume", "pore.volume")
+        dict.__setitem__(self, "pore.ic", np.full(self.Np, np.nan))
+
+    def run(self, x0, tspan, saveat=None, integrator=None):
+        """Same signature and `saveat` handling as the reference (:51-99)."""
+        from .integrators import B200RK45
+        if np.isscalar(saveat):
+            saveat = np.arange(*tspan, saveat)
+        if (saveat is not None) and (tspan[1] not in saveat):
+            saveat = np.hstack((saveat, [tspan[1]]))
+        integrator = B200RK45() if integrator is None else integrator
+        if not getattr(integrator, "_b200_native", False):
+            raise TypeError("openpnm_b200 transient algorithms need a B200RK45 integrator")
+        self._validate_settings()
+        ctx = integrator.ctx
+        self._ctx = ctx
+        ctx.set_format(integrator._fmt_code())
+        if self.settings["validate_topology"]:
+            self._validate_topology_health(ctx)
+        x0 = np.ones(self.Np, dtype=float) * x0
+        dict.__setitem__(self, "pore.ic", x0)
+        bc = ~np.isnan(self["pore.bc.value"])            # _merge_inital_and_boundary_values
+        x0[bc] = self["pore.bc.value"][bc]
+        q = self.settings["quantity"]
+        dict.__setitem__(self, q, x0)
+        V = np.asarray(self.network[self.settings["pore_volume"]], dtype=np.float64)
+        V = V * np.ones(self.Np)
+        try:
+            self._assemble(ctx)
+            ctx.clear_sources()
+            for mask, kind, p1, p2, p3 in self._sources():
+                ctx.add_source(kind, mask, p1, p2, p3)
+            cap = None
+            if saveat is None:
+                cap = integrator.max_saved or max(16, min(20000, int(2e9 // (8 * self.Np))))
+            t, Y, nsteps, nfev, status = ctx.transient_rk45(
+                x0, V, float(tspan[0]), float(tspan[1]), rtol=integrator.rtol,
+                atol=integrator.atol, saveat=saveat, capacity=cap)
+        except _lib.B200Error as e:
+            if e.code == -4:
+                raise Exception("A or b contains inf/nan values") from e
+            raise
+        if status == -1:
+            raise Exception("Required step size is less than spacing between numbers.")
+        if status == -2:
+            raise Exception("too many accepted steps to store them all: pass `saveat`")
+        Yh = np.ascontiguousarray(Y.T.cpu().numpy())
+        self.soln = SolutionContainer()
+        self.soln[q] = TransientSolution(t, Yh)
+        self.soln.nsteps, self.soln.nfev = int(nsteps), int(nfev)
+        if Yh.shape[1]:
+            dict.__setitem__(self, q, Yh[:, -1].copy())
+            self._x_dev = Y[-1]
+        self.stats = ctx.stats()
+        self._post_run(self[q])
+
+
+class TransientFickianDiffusion(TransientReactiveTransport):
+    """_transient_fickian_diffusion.py"""
+
+    def __init__(self, network, phase, name="trans_fick_?", **kwargs):
+        super().__init__(network=network, phase=phase, name=name, **kwargs)
+        self.settings._update(dict(quantity="pore.concentration",
+                                   conductance="throat.diffusive_conductance"))
+        self.settings._update(kwargs)
+
+
+class TransientOhmicConduction(TransientReactiveTransport):
+    """_transient_ohmic_conduction.py"""
+
+    def __init__(self, network, phase, name="trans_ohmic_?", **kwargs):
+        super().__init__(network=network, phase=phase, name=name, **kwargs)
+        self.settings._update(dict(quantity="pore.voltage",
+                                   conductance="throat.electrical_conductance"))
+        self.settings._update(kwargs)
+
+
+class TransientFourierConduction(TransientReactiveTransport):
+    """_transient_fourier_conduction.py"""
+
+    def __init__(self, network, phase, name="trans_fourier_?", **kwargs):
+        super().__init__(network=network, phase=phase, name=name, **kwargs)
+        self.settings._update(dict(quantity="pore.temperature",
+                                   conductance="throat.thermal_conductance"))
+        self.settings._update(kwargs)
 
 
 class StokesFlow(ReactiveTransport):

@@ -830,6 +830,13 @@ static int launch_spmv_dot(b200_ctx* ctx, const double* p_owned, const double* r
   return B200_OK;
 }
 
+// out = A~ w on the prepared operator (w, out: owned pointers of padded vectors);
+// the dot products K_A makes on the side land in a scratch group
+int b200_apply_operator(b200_ctx* ctx, const double* w_owned, double* out_owned) {
+  return launch_spmv_dot(ctx, w_owned, ctx->vr.as<double>() + ctx->pad, out_owned,
+                         ctx->scal.as<double>() + SC_AUX0);
+}
+
 extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol,
                         int64_t maxiter, double* x, int64_t* iters, double* relres, int* info) {
   if (!ctx || !ctx->have_sys || !x) {

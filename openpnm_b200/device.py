@@ -247,6 +247,30 @@ class Context:
                                       C.byref(conv), C.byref(cgt), C.byref(info)))
         return x, ni.value, bool(conv.value), cgt.value, info.value
 
+    def transient_rk45(self, x0, volume, t0, t1, rtol=1e-6, atol=1e-6, saveat=None,
+                       capacity=None):
+        """(times ndarray, states device tensor [len(times), n], nsteps, nfev, status)"""
+        torch = _torch()
+        x0 = self.to_device(x0, torch.float64)
+        vol = self.to_device(volume, torch.float64)
+        if saveat is None:
+            sv = np.zeros(0)
+            cap = int(capacity or 4096)
+        else:
+            sv = np.ascontiguousarray(saveat, dtype=np.float64)
+            cap = int(sv.size)
+        with torch.cuda.stream(self.stream):
+            out = torch.empty((max(cap, 1), self.n), dtype=torch.float64, device=self.tdev)
+        times = np.zeros(max(cap, 1))
+        nout, nsteps, nfev, status = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        self._ck(self.lib.b200_transient_rk45(
+            self._h, self._p(x0), self._p(vol), float(t0), float(t1), float(rtol), float(atol),
+            _lib.np_ptr(sv) if sv.size else C.c_void_p(), int(sv.size), max(cap, 1),
+            self._p(out), _lib.np_ptr(times), C.byref(nout), C.byref(nsteps), C.byref(nfev),
+            C.byref(status)))
+        k = nout.value
+        return times[:k].copy(), out[:k], nsteps.value, nfev.value, status.value
+
     def rate_pores(self, x, pores):
         torch = _torch()
         x = self.to_device(x, torch.float64)

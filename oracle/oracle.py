@@ -30,7 +30,7 @@ import scipy.sparse.linalg as spla
 __all__ = [
     "cubic_network", "adjacency_coo", "laplacian_coo", "build_A", "apply_bcs",
     "apply_sources", "to_csr", "source_term", "picard_run", "rate",
-    "jacobi_pcg", "spsolve", "transport_run", "delaunay_network",
+    "jacobi_pcg", "spsolve", "transport_run", "delaunay_network", "transient_run",
 ]
 
 
@@ -348,6 +348,39 @@ def transport_run(conns, g, Np, bc_value=None, bc_rate=None, solver=None, x0=Non
     there are no sources; num_iter == 1 for a converged direct solve)."""
     out = picard_run(conns, g, Np, bc_value, bc_rate, (), x0, solver)
     return out
+
+
+def transient_run(conns, g, Np, volume, x0, tspan, saveat=None, bc_value=None, bc_rate=None,
+                  sources=(), rtol=1e-6, atol=1e-6):
+    """`TransientReactiveTransport.run` with `ScipyRK45`
+    (openpnm/algorithms/_transient_reactive_transport.py:51-123,
+    openpnm/integrators/_scipy.py:18-56): dy/dt = (-A y + b) / V with A, b
+    re-assembled (BCs + sources linearised at y) at every right-hand-side call,
+    integrated by scipy.integrate.solve_ivp(method="RK45", t_eval=saveat).
+    Returns (t, Y) with Y of shape (Np, len(t)) as SciPy does."""
+    from scipy.integrate import solve_ivp
+    if np.isscalar(saveat):
+        saveat = np.arange(*tspan, saveat)
+    if (saveat is not None) and (tspan[1] not in saveat):
+        saveat = np.hstack((saveat, [tspan[1]]))
+    y0 = np.ones(Np, dtype=float) * x0
+    if bc_value is not None:                      # _merge_inital_and_boundary_values
+        m = ~np.isnan(bc_value)
+        y0[m] = bc_value[m]
+    pure = build_A(conns, g, Np)
+    V = np.asarray(volume, dtype=float) * np.ones(Np)
+
+    def ode_func(t, y):
+        A, b, _ = apply_bcs(pure, Np, bc_value, bc_rate)
+        lin = [(mask, *source_term(kind, y, params)[:2]) for mask, kind, params in sources]
+        if lin:
+            A, b = apply_sources(A, b, Np, lin)
+        return (-(to_csr(A, Np) @ y) + b) / V
+
+    sol = solve_ivp(ode_func, tspan, y0, method="RK45", atol=atol, rtol=rtol, t_eval=saveat)
+    if not sol.success:
+        raise Exception(sol.message)
+    return sol.t, sol.y
 
 
 def rate(conns, g, x, pores=None, throats=None, mode="group"):

@@ -360,6 +360,68 @@ def g11_irregular():
     save("g12_delaunay_600_coords", coords=np.array(dn["pore.coords"]))
 
 
+def g13_transient():
+    # tests/unit/algorithms/TransientFickianDiffusionTest.py:8-36 (volume, g, BCs as there)
+    from openpnm.models.physics import source_terms
+    pn = op.network.Cubic(shape=[4, 3, 1], spacing=1.0)
+    pn["pore.volume"] = 1e-14
+    ph = op.phase.Phase(network=pn)
+    ph["throat.diffusive_conductance"] = 1e-15
+    alg = op.algorithms.TransientFickianDiffusion(network=pn, phase=ph)
+    alg.settings._update({"quantity": "pore.concentration",
+                          "conductance": "throat.diffusive_conductance"})
+    alg.set_value_BC(pores=pn.pores("right"), values=1)
+    alg.set_value_BC(pores=pn.pores("left"), values=0)
+    alg.run(x0=0, tspan=(0, 10))
+    assert np.isclose(alg.x.mean(), 0.40803, rtol=1e-5)
+    x10 = np.array(alg.x)
+    alg.run(x0=0, tspan=(0, 200))
+    assert np.isclose(alg.x.mean(), 0.5, rtol=1e-5)
+    x200 = np.array(alg.x)
+    save("g13_transient_4x3x1", conns=pn["throat.conns"].astype(np.int64),
+         bc_value=np.array(alg["pore.bc.value"], dtype=float), x10=x10, x200=x200)
+    META["g13_transient_4x3x1"] = dict(x10_mean=float(x10.mean()), x200_mean=float(x200.mean()))
+    # heterogeneous 8x7x6 with a power-law sink, saved at given times
+    pn = op.network.Cubic(shape=[8, 7, 6], spacing=1e-4)
+    rng = np.random.default_rng(7)
+    pn["pore.volume"] = rng.uniform(0.5, 2.0, pn.Np) * 1e-13
+    ph = op.phase.Phase(network=pn)
+    ph["throat.diffusive_conductance"] = 10.0 ** rng.uniform(-15, -13, pn.Nt)
+    ph["pore.A1"], ph["pore.A2"], ph["pore.A3"] = -2e-14, 1.5, 0.0
+    ph.add_model(propname="pore.rxn", model=source_terms.power_law, A1="pore.A1", A2="pore.A2",
+                 A3="pore.A3", X="pore.concentration", regen_mode="deferred")
+    alg = op.algorithms.TransientFickianDiffusion(network=pn, phase=ph)
+    alg.settings._update({"quantity": "pore.concentration",
+                          "conductance": "throat.diffusive_conductance"})
+    alg.set_value_BC(pores=pn.pores("left"), values=1.0)
+    src = np.setdiff1d(pn.Ps, pn.pores("left"))
+    alg.set_source(pores=src, propname="pore.rxn")
+    saveat = np.array([0.0, 0.5, 1.0, 2.5, 5.0])
+    alg.run(x0=0.2, tspan=(0, 5.0), saveat=saveat,
+            integrator=op.integrators.ScipyRK45(atol=1e-8, rtol=1e-8))
+    sol = alg.soln["pore.concentration"]
+    t_ref, Y_ref = np.array(sol.t), np.array(sol)
+    mask = np.zeros(pn.Np, dtype=bool)
+    mask[src] = True
+    gv = np.array(ph["throat.diffusive_conductance"], dtype=float)
+    t_o, Y_o = oracle.transient_run(pn["throat.conns"], gv, pn.Np, np.array(pn["pore.volume"]),
+                                    0.2, (0, 5.0), saveat=saveat,
+                                    bc_value=np.array(alg["pore.bc.value"], dtype=float),
+                                    sources=[(mask, "power_law",
+                                              {"A1": -2e-14, "A2": 1.5, "A3": 0.0})],
+                                    rtol=1e-8, atol=1e-8)
+    assert np.array_equal(t_o, t_ref)
+    assert np.allclose(Y_o, Y_ref, rtol=1e-10, atol=0), np.max(np.abs(Y_o - Y_ref))
+    save("g13_transient_8x7x6_power_law", conns=pn["throat.conns"].astype(np.int64), g=gv,
+         volume=np.array(pn["pore.volume"]), bc_value=np.array(alg["pore.bc.value"], dtype=float),
+         src_pores=src.astype(np.int64), t=t_ref, Y=Y_ref)
+    META["g13_transient_8x7x6_power_law"] = dict(
+        x0=0.2, tspan=[0.0, 5.0], rtol=1e-8, atol=1e-8,
+        source=dict(kind="power_law", params={"A1": -2e-14, "A2": 1.5, "A3": 0.0}),
+        y_end_mean=float(Y_ref[:, -1].mean()))
+    print("g13", META["g13_transient_4x3x1"], META["g13_transient_8x7x6_power_law"])
+
+
 def g8_big():
     # config 1 scale: Cubic 50^3, SuperLU (~3 min)
     n = 50
@@ -381,7 +443,7 @@ if __name__ == "__main__":
     if os.path.exists(meta_path):
         META.update(json.load(open(meta_path)))
     cases = [g1_solvers, g2_stokes, g3_reactive, g4_csr, g5_conduit, g6_profiles,
-             g7_hetero, g11_irregular]
+             g7_hetero, g11_irregular, g13_transient]
     if args.big:
         cases = [g8_big]
     for fn in cases:

@@ -122,3 +122,25 @@ def test_jacobi_pcg_oracle_matches_direct(golden):
     x, info, its = oracle.jacobi_pcg(M, g["b"], rtol=1e-13)
     assert info == 0 and its > 10
     np.testing.assert_allclose(x, g["x"], rtol=1e-8, atol=0)
+
+
+def test_transient_oracle_against_reference(golden, golden_meta):
+    """TransientFickianDiffusionTest.py:8-36 and a heterogeneous power-law case."""
+    g = golden("g13_transient_4x3x1")
+    net = oracle.cubic_network([4, 3, 1])
+    assert np.array_equal(net["conns"], g["conns"])
+    t, Y = oracle.transient_run(net["conns"], 1e-15 * np.ones(net["Nt"]), net["Np"], 1e-14, 0.0,
+                                (0, 10), bc_value=g["bc_value"])
+    np.testing.assert_allclose(Y[:, -1], g["x10"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(Y[:, -1].mean(), 0.40803, rtol=1e-5)
+    g = golden("g13_transient_8x7x6_power_law")
+    m = golden_meta["g13_transient_8x7x6_power_law"]
+    Np = g["volume"].size
+    mask = np.zeros(Np, dtype=bool)
+    mask[g["src_pores"]] = True
+    t, Y = oracle.transient_run(g["conns"], g["g"], Np, g["volume"], m["x0"], tuple(m["tspan"]),
+                                saveat=g["t"], bc_value=g["bc_value"],
+                                sources=[(mask, m["source"]["kind"], m["source"]["params"])],
+                                rtol=m["rtol"], atol=m["atol"])
+    assert np.array_equal(t, g["t"])
+    np.testing.assert_allclose(Y, g["Y"], rtol=1e-10, atol=0)
