@@ -300,6 +300,8 @@ class Transport(dict):
         dict.__setitem__(self, "pore.initial_guess", x0)
         self.soln = SolutionContainer()
         self.soln.is_converged = False
+        if self._world_size() > 1 and getattr(solver, "distributed", True):
+            return self._run_slabs(solver, x0, x0_given)
         ctx = solver.ctx
         self._ctx = ctx
         ctx.set_format(solver._fmt_code())
@@ -340,6 +342,75 @@ class Transport(dict):
     def _post_run(self, x):
         pass
 
+    @staticmethod
+    def _world_size():
+        try:
+            import torch.distributed as dist
+            return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        except Exception:
+            return 1
+
+    def _run_slabs(self, solver, x0, x0_given):
+        """The same `run()` under torchrun (one process per GPU): every rank holds the
+        network as OpenPNM does, assembles the rows of its slab of the index-ordered
+        pores from the throats touching them, the PCG runs slab-parallel
+        (csrc/dist.cu, csrc/p2p.cu) and every rank receives the full solution
+        (the algorithm of openpnm/solvers/_petsc.py:117-128,160,225)."""
+        import torch
+        import torch.distributed as dist
+        from . import dist as bdist
+        if self._sources():
+            raise NotImplementedError("source terms are not supported in slab-parallel runs yet")
+        world, rank = dist.get_world_size(), dist.get_rank()
+        conns = np.asarray(self.network["throat.conns"], dtype=np.int64)
+        g = self._conductance()
+        band = bdist.bandwidth(conns)
+        shape = getattr(self.network, "shape", None)
+        if shape is not None and len(shape) == 3 and int(np.prod(shape)) == self.Np:
+            ranges = bdist.cubic_slab_ranges(shape, world)
+        else:
+            ranges = bdist.slab_ranges(self.Np, world)
+        if min(e - b for b, e in ranges) < band:
+            raise Exception(f"a slab would be thinner than the matrix half-bandwidth ({band}); "
+                            "renumber the pores by coordinate (openpnm_b200.dist.coordinate_order) "
+                            "or use fewer ranks")
+        rb, re = ranges[rank]
+        key = (id(self.network), world, rank, solver.device, solver.fmt)
+        ss = getattr(solver, "_slab", None)
+        if ss is None or getattr(solver, "_slab_key", None) != key:
+            ss = bdist.SlabSolver(self.Np, rb, re, device=solver.device, fmt=solver.fmt)
+            solver._slab, solver._slab_key, solver._slab_p2p = ss, key, None
+        ctx = ss.ctx
+        self._ctx, self._slab = ctx, ss
+        if self.settings["validate_topology"]:
+            self._validate_topology_health(ctx)
+        mask = bdist.slab_throat_mask(conns, rb, re)
+        try:
+            ss.assemble(conns[mask], g[mask], self["pore.bc.value"], self["pore.bc.rate"])
+            if solver._slab_p2p is None:
+                solver._slab_p2p = ss.enable_p2p()
+            x0_loc = x0[rb:re] if x0_given else None
+            x_loc, cg_iters, relres, info = ss.solve(
+                rtol=solver.tol, maxiter=0 if solver.maxiter is None else solver.maxiter,
+                x0=x0_loc)
+        except _lib.B200Error as e:
+            if e.code == -4:
+                raise Exception("A or b contains inf/nan values") from e
+            raise
+        x_dev = ss.gather(x_loc)
+        self._x_dev = x_dev
+        x = x_dev.cpu().numpy()
+        q = self.settings["quantity"]
+        dict.__setitem__(self, q, x)
+        self.soln[q] = SteadyStateSolution(x)
+        # linear problem: one solve, judged like the reference's second residual check
+        self.soln.is_converged = info == 0 and solver.tol <= self.settings.get("f_rtol", 1e-6)
+        self.soln.num_iter = 1
+        self.soln.cg_iters = int(cg_iters)
+        self.soln.exit_code = int(info)
+        self.soln.relres = float(relres)
+        self.stats = ctx.stats()
+
     def _download(self, ctx, x_dev):
         """Device -> host through a page-locked staging buffer (kept per size)."""
         import torch
@@ -378,6 +449,8 @@ class Transport(dict):
         if self._ctx is None:
             raise Exception("run() first")
         x = self._x_dev if self._x_dev is not None else self.x
+        if getattr(self, "_slab", None) is not None and self._world_size() > 1:
+            return self._rate_slabs(x, pores, throats, mode)
         if throats.size:
             R = self._ctx.rate_throats(x, throats).cpu().numpy()
         else:
@@ -385,6 +458,31 @@ class Transport(dict):
         if mode == "group":
             R = np.sum(R)
         return np.array(R, ndmin=1)
+
+
+def _rate_slabs(self, x, pores, throats, mode):
+    """rate() in a slab-parallel run: every rank evaluates the pores it owns, the
+    per-pore values are summed over ranks (each pore is owned exactly once)."""
+    import torch
+    import torch.distributed as dist
+    ss = self._slab
+    if throats.size:
+        conns = np.asarray(self.network["throat.conns"], dtype=np.int64)[throats]
+        g = self._conductance()[throats]
+        xh = x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
+        R = np.abs(g * (xh[conns[:, 1]] - xh[conns[:, 0]]))      # trivial gather on the full x
+        return np.array(np.sum(R) if mode == "group" else R, ndmin=1)
+    out = torch.zeros(pores.size, dtype=torch.float64, device=ss.ctx.tdev)
+    mine = np.flatnonzero((pores >= ss.row_begin) & (pores < ss.row_end))
+    if mine.size:
+        out[torch.from_numpy(mine).to(ss.ctx.tdev)] = ss.ctx.rate_pores(x, pores[mine])
+    ss.ctx.synchronize()
+    dist.all_reduce(out)
+    R = out.cpu().numpy()
+    return np.array(np.sum(R) if mode == "group" else R, ndmin=1)
+
+
+Transport._rate_slabs = _rate_slabs
 
 
 class ReactiveTransport(Transport):

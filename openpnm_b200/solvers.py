@@ -58,8 +58,11 @@ class B200PCG(IterativeSolver):
     maxiter : int or None
         ``None`` means ``10 * n``, which is what `ScipyCG` effectively uses
         (it never forwards ``self.maxiter``; SciPy's default applies).
-    device : int
-        CUDA device ordinal.
+    device : int or None
+        CUDA device ordinal; ``None`` means ``LOCAL_RANK`` (torchrun) or 0.
+    distributed : bool
+        With ``torch.distributed`` initialised (torchrun, one process per GPU),
+        ``openpnm_b200`` algorithms split the network into slabs over the ranks.
     fmt : {'auto', 'csr', 'dia'}
         Operator storage; 'auto' picks symmetric-diagonal storage when the
         matrix has at most 8 distinct super-diagonals (lattice networks).
@@ -70,10 +73,14 @@ class B200PCG(IterativeSolver):
 
     _b200_native = True
 
-    def __init__(self, tol=1e-8, maxiter=None, device=0, fmt="auto"):
+    def __init__(self, tol=1e-8, maxiter=None, device=None, fmt="auto", distributed=True):
         super().__init__(tol=tol, maxiter=maxiter)
+        if device is None:          # under torchrun: one process per GPU
+            import os
+            device = int(os.environ.get("LOCAL_RANK", "0"))
         self.device = device
         self.fmt = fmt
+        self.distributed = distributed   # slab-parallel `alg.run()` when torch.distributed is up
         self._ctx = None
         self.info = {}
 

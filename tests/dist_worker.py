@@ -84,6 +84,31 @@ def main():
                 print(f"dist ok shape={shape} fmt={fmt} world={world} iters={it} err={err:.2e} "
                       f"p2p={p2p} fmtcode={ss.ctx.pcg_format()}", flush=True)
             ss.ctx.close()
+    # ---- the algorithm API under torchrun: the same script, slab-parallel run()
+    import openpnm_b200 as b2
+    shape = (16, 9, 10)
+    pn = b2.Cubic(shape, spacing=1e-4)
+    ph = b2.Phase(pn)
+    g = 10.0 ** np.random.default_rng(5).uniform(-15, -12, pn.Nt)
+    ph["throat.hydraulic_conductance"] = g
+    sf = b2.StokesFlow(network=pn, phase=ph)
+    sf.set_value_BC(pores=pn.pores("left"), values=2e5)
+    sf.set_value_BC(pores=pn.pores("right"), values=1e5)
+    sf.run(solver=b2.B200PCG(tol=1e-13))
+    ref = oracle.transport_run(pn.conns, g, pn.Np, bc_value=sf["pore.bc.value"])
+    err = np.max(np.abs(sf.x - ref["x"]) / np.abs(ref["x"]))
+    assert sf.soln.is_converged and err < 1e-8, err
+    q = sf.rate(pores=pn.pores("left"))[0]
+    qref = oracle.rate(pn.conns, g, ref["x"], pores=pn.pores("left"))[0]
+    assert abs(q - qref) <= 1e-8 * abs(qref)
+    qs = sf.rate(pores=pn.pores("right"), mode="single")
+    assert qs.size == pn.pores("right").size and abs(qs.sum() + q) <= 1e-8 * abs(q)
+    qt = sf.rate(throats=[0, 5, 17], mode="single")
+    np.testing.assert_allclose(qt, oracle.rate(pn.conns, g, ref["x"], throats=[0, 5, 17],
+                                               mode="single"), rtol=1e-8)
+    if rank == 0:
+        print(f"dist ok algorithm-API world={world} err={err:.2e} cg_iters={sf.soln.cg_iters} "
+              f"p2p={getattr(sf, '_slab', None) is not None}", flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
