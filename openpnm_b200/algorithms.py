@@ -359,8 +359,6 @@ class Transport(dict):
         import torch
         import torch.distributed as dist
         from . import dist as bdist
-        if self._sources():
-            raise NotImplementedError("source terms are not supported in slab-parallel runs yet")
         world, rank = dist.get_world_size(), dist.get_rank()
         conns = np.asarray(self.network["throat.conns"], dtype=np.int64)
         g = self._conductance()
@@ -386,13 +384,24 @@ class Transport(dict):
             self._validate_topology_health(ctx)
         mask = bdist.slab_throat_mask(conns, rb, re)
         try:
-            ss.assemble(conns[mask], g[mask], self["pore.bc.value"], self["pore.bc.rate"])
-            if solver._slab_p2p is None:
+            srcs = self._sources()
+            f, nnz0, nnz = ss.assemble(conns[mask], g[mask], self["pore.bc.value"],
+                                       self["pore.bc.rate"], keep_zero_diag=len(srcs) > 0)
+            ctx.clear_sources()
+            if solver._slab_p2p is None:              # maps the peers once (source-free operator)
                 solver._slab_p2p = ss.enable_p2p()
-            x0_loc = x0[rb:re] if x0_given else None
-            x_loc, cg_iters, relres, info = ss.solve(
-                rtol=solver.tol, maxiter=0 if solver.maxiter is None else solver.maxiter,
-                x0=x0_loc)
+            for smask, kind, p1, p2, p3 in srcs:      # per-pore arrays of the owned rows
+                loc = [None if p is None else
+                       (p[rb:re] if np.ndim(p) else np.full(re - rb, float(p))) for p in (p1, p2, p3)]
+                ctx.add_source(kind, smask[rb:re], *loc)
+            s = self.settings
+            cg_rtol = s["cg_rtol"] if s.get("cg_rtol") else solver.tol
+            x_loc, num_iter, conv, cg_iters, info = ctx.picard(
+                x0=x0[rb:re] if x0_given else None,
+                relaxation=s.get("relaxation_factor", 1.0),
+                newton_maxiter=s.get("newton_maxiter", 5000),
+                f_rtol=s.get("f_rtol", 1e-6), x_rtol=s.get("x_rtol", 1e-6),
+                cg_rtol=cg_rtol, cg_maxiter=0 if solver.maxiter is None else solver.maxiter)
         except _lib.B200Error as e:
             if e.code == -4:
                 raise Exception("A or b contains inf/nan values") from e
@@ -403,13 +412,13 @@ class Transport(dict):
         q = self.settings["quantity"]
         dict.__setitem__(self, q, x)
         self.soln[q] = SteadyStateSolution(x)
-        # linear problem: one solve, judged like the reference's second residual check
-        self.soln.is_converged = info == 0 and solver.tol <= self.settings.get("f_rtol", 1e-6)
-        self.soln.num_iter = 1
+        self.soln.is_converged = bool(conv)
+        self.soln.num_iter = int(num_iter)
         self.soln.cg_iters = int(cg_iters)
         self.soln.exit_code = int(info)
-        self.soln.relres = float(relres)
         self.stats = ctx.stats()
+        self.soln.relres = self.stats["relres"]
+        self._post_run(x)
 
     def _download(self, ctx, x_dev):
         """Device -> host through a page-locked staging buffer (kept per size)."""

@@ -88,7 +88,19 @@ extern "C" int b200_picard(b200_ctx* ctx, const double* x0, double relaxation,
     CK(cudaMemcpyAsync(ctx->flags_h, flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost,
                        ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->flags_h[FLAG_NONFINITE]) FAIL(B200_ERR_NONFINITE, "x0 contains inf/nan values");
+    bool bad = ctx->flags_h[FLAG_NONFINITE] != 0;
+    if (ctx->nranks > 1) {            // same verdict on every rank
+      double* sc = ctx->scal.as<double>();
+      ctx->scal_h[SC_AUX2] = bad ? 1.0 : 0.0;
+      CK(cudaMemcpyAsync(sc + SC_AUX2, ctx->scal_h + SC_AUX2, sizeof(double),
+                         cudaMemcpyHostToDevice, ctx->stream));
+      RET(b200_allreduce_sum(ctx, sc + SC_AUX2, 1));
+      CK(cudaMemcpyAsync(ctx->scal_h + SC_AUX2, sc + SC_AUX2, sizeof(double),
+                         cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      bad = ctx->scal_h[SC_AUX2] > 0.0;
+    }
+    if (bad) FAIL(B200_ERR_NONFINITE, "x0 contains inf/nan values");
   } else {
     CK(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), ctx->stream));
   }
@@ -112,7 +124,8 @@ extern "C" int b200_picard(b200_ctx* ctx, const double* x0, double relaxation,
     CK(cudaMemcpyAsync(ctx->flags_h, flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost,
                        ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->flags_h[FLAG_NONFINITE] || !isfinite(fn))
+    // (in slab mode a local inf/nan shows up in the all-reduced norms on every rank)
+    if ((ctx->nranks == 1 && ctx->flags_h[FLAG_NONFINITE]) || !isfinite(fn))
       FAIL(B200_ERR_NONFINITE, "A or b contains inf/nan values");
     int64_t its = 0;
     double rel = 0.0;
@@ -121,6 +134,7 @@ extern "C" int b200_picard(b200_ctx* ctx, const double* x0, double relaxation,
     double* sc = ctx->scal.as<double>();
     LAUNCH(ctx, k_relax, grid_for(n, 256, 2), 256, 0, x, xnew, relaxation, n,
            ctx->w_part.as<double>(), ctx->w_ticket.as<unsigned>(), sc + SC_AUX0, flags);
+    RET(b200_allreduce_sum(ctx, sc + SC_AUX0, 1));     // slab mode: global ||dx||^2
     CK(cudaMemcpyAsync(ctx->scal_h + SC_AUX0, sc + SC_AUX0, sizeof(double), cudaMemcpyDeviceToHost,
                        ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -156,12 +156,15 @@ int b200_linearize(b200_ctx* ctx, const double* x) {
   return B200_OK;
 }
 
-// residual R = A x - b with the current linearisation; returns ||R||^2, ||x||^2
+// residual R = A x - b with the current linearisation; returns ||R||^2, ||x||^2.
+// xcol is indexed by (global) column, xrow by local row -- the same pointer on
+// one GPU; in slab mode xcol points into a halo-exchanged padded copy of x.
 __global__ void __launch_bounds__(256) k_residual_norms(const int* __restrict__ indptr,
                                                         const int* __restrict__ indices,
                                                         const double* __restrict__ data,
                                                         const double* __restrict__ b,
-                                                        const double* __restrict__ x, int64_t n,
+                                                        const double* __restrict__ xcol,
+                                                        const double* __restrict__ xrow, int64_t n,
                                                         double* part, unsigned* ticket,
                                                         double* out_r2, double* out_x2) {
   constexpr int G = 8;
@@ -173,14 +176,14 @@ __global__ void __launch_bounds__(256) k_residual_norms(const int* __restrict__ 
     double s = 0.0;
     if (r < n) {
       const int e1 = indptr[r + 1];
-      for (int e = indptr[r] + lane; e < e1; e += G) s += data[e] * x[indices[e]];
+      for (int e = indptr[r] + lane; e < e1; e += G) s += data[e] * xcol[indices[e]];
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, G);
     if (lane == 0 && r < n) {
       const double res = s - b[r];
       r2 += res * res;
-      x2 += x[r] * x[r];
+      x2 += xrow[r] * xrow[r];
     }
   }
   double v[2] = {r2, x2};
@@ -191,9 +194,21 @@ __global__ void __launch_bounds__(256) k_residual_norms(const int* __restrict__ 
 int b200_residual_norms(b200_ctx* ctx, const double* x, double* res2, double* x2) {
   RET(ensure_ws(ctx));
   double* sc = ctx->scal.as<double>();
+  const double* xcol = x;
+  if (ctx->nranks > 1) {
+    // slab: columns are global ids; gather from a padded copy of x whose halo
+    // windows the neighbour ranks fill (the PCG's x buffer is free between solves)
+    RET(b200_pcg_prepare(ctx, ctx->force_fmt));
+    double* xo = owned(ctx->vx, ctx->pad);
+    CK(cudaMemcpyAsync(xo, x, (size_t)ctx->n * sizeof(double), cudaMemcpyDeviceToDevice,
+                       ctx->stream));
+    RET(b200_halo_exchange(ctx, ctx->vx.as<double>()));
+    xcol = xo - ctx->row_begin;
+  }
   LAUNCH(ctx, k_residual_norms, grid_for(ctx->n * 8, 256), 256, 0, ctx->sys_indptr.as<int>(),
-         ctx->sys_indices.as<int>(), ctx->sys_data.as<double>(), cur_b(ctx), x, ctx->n,
+         ctx->sys_indices.as<int>(), ctx->sys_data.as<double>(), cur_b(ctx), xcol, x, ctx->n,
          ctx->w_part.as<double>(), ctx->w_ticket.as<unsigned>(), sc + SC_AUX0, sc + SC_AUX1);
+  RET(b200_allreduce_sum(ctx, sc + SC_AUX0, 2));
   CK(cudaMemcpyAsync(ctx->scal_h + SC_AUX0, sc + SC_AUX0, 2 * sizeof(double),
                      cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -366,7 +381,11 @@ __global__ void k_rowstart(const int* __restrict__ optr, int64_t n, int64_t Q, i
 static int prepare_operator(b200_ctx* ctx) {
   const int64_t n = ctx->n;
   RET(ensure_ws(ctx));
-  if (!ctx->lin_valid) RET(b200_linearize(ctx, nullptr));   // no sources: trivial
+  if (!ctx->lin_valid) {
+    if (ctx->srcs.n > 0)
+      FAIL(B200_ERR_ARG, "sources are registered but not linearised: call b200_picard");
+    RET(b200_linearize(ctx, nullptr));   // no sources: trivial
+  }
   CK(cudaMemsetAsync(ctx->w_flags.p, 0, FLAG_COUNT * sizeof(int), ctx->stream));
   int* flags = ctx->w_flags.as<int>();
   const int* indptr = ctx->sys_indptr.as<int>();
@@ -890,7 +909,11 @@ extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double ato
   CK(cudaMemcpyAsync(ctx->flags_h, flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost,
                      ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  if (ctx->flags_h[FLAG_NONFINITE]) FAIL(B200_ERR_NONFINITE, "b or x0 contains inf/nan values");
+  // every rank must take the same decision: in slab mode judge by the all-reduced
+  // norms (an inf/nan anywhere makes them non-finite everywhere)
+  if ((!multi && ctx->flags_h[FLAG_NONFINITE]) || !isfinite(ctx->scal_h[SC_BNORM]) ||
+      !isfinite(ctx->scal_h[G_TRUE]))
+    FAIL(B200_ERR_NONFINITE, "b or x0 contains inf/nan values");
 
   const double bnorm2 = ctx->scal_h[SC_BNORM];
   double tol2 = rtol * rtol * bnorm2;

@@ -170,7 +170,7 @@ class SlabSolver:
             self.ctx._ck(self.ctx.lib.b200_comm_init(self.ctx._h, self.world, self.rank,
                                                      C.cast(idbuf, C.c_void_p)))
 
-    def assemble(self, conns_local, g_local, bc_value=None, bc_rate=None):
+    def assemble(self, conns_local, g_local, bc_value=None, bc_rate=None, keep_zero_diag=False):
         import torch
         import torch.distributed as dist
         ctx = self.ctx
@@ -183,7 +183,7 @@ class SlabSolver:
             dist.all_reduce(t)          # f = global mean of the pure diagonal
             t = t.cpu()
             ctx.set_diag_mean(float(t[0] / t[1]))
-        f, nnz_sys = ctx.apply_bcs(bc_value, bc_rate)
+        f, nnz_sys = ctx.apply_bcs(bc_value, bc_rate, keep_zero_diag=keep_zero_diag)
         return f, nnz, nnz_sys
 
     def enable_p2p(self):

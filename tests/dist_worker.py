@@ -109,6 +109,30 @@ def main():
     if rank == 0:
         print(f"dist ok algorithm-API world={world} err={err:.2e} cg_iters={sf.soln.cg_iters} "
               f"p2p={getattr(sf, '_slab', None) is not None}", flush=True)
+    # nonlinear source, Picard loop slab-parallel
+    ph["throat.diffusive_conductance"] = g
+    ph["pore.A1"], ph["pore.A2"], ph["pore.A3"] = -1e-13, 2.0, 0.0
+    ph.add_model(propname="pore.rxn", model="power_law", X="pore.concentration",
+                 A1="pore.A1", A2="pore.A2", A3="pore.A3")
+    rt = b2.ReactiveTransport(network=pn, phase=ph)
+    rt.settings._update({"quantity": "pore.concentration",
+                         "conductance": "throat.diffusive_conductance"})
+    left = pn.pores("left")
+    rt.set_value_BC(pores=left, values=1.0)
+    src = np.setdiff1d(pn.Ps, left)
+    rt.set_source(pores=src, propname="pore.rxn")
+    rt.run(solver=b2.B200PCG(tol=1e-12))
+    smask = np.zeros(pn.Np, dtype=bool)
+    smask[src] = True
+    refp = oracle.picard_run(pn.conns, g, pn.Np, bc_value=rt["pore.bc.value"],
+                             sources=[(smask, "power_law", {"A1": -1e-13, "A2": 2.0, "A3": 0.0})])
+    assert rt.soln.is_converged and rt.soln.num_iter == refp["num_iter"], \
+        (rt.soln.num_iter, refp["num_iter"])
+    errp = np.max(np.abs(rt.x - refp["x"])) / np.max(np.abs(refp["x"]))
+    assert errp < 1e-8, errp
+    if rank == 0:
+        print(f"dist ok reactive world={world} num_iter={rt.soln.num_iter} err={errp:.2e}",
+              flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
