@@ -14,7 +14,7 @@ Only the hot path lives here; everything needs a CUDA device
 and the in-tree libb200pnm.so -- there is no CPU fallback.
 """
 from . import _lib, algorithms, integrators, network, solvers
-from .algorithms import (FickianDiffusion, FourierConduction, OhmicConduction,
+from .algorithms import (AdvectionDiffusion, FickianDiffusion, FourierConduction, OhmicConduction,
                          ReactiveTransport, StokesFlow, TransientFickianDiffusion,
                          TransientReactiveTransport, Transport)
 from .integrators import B200RK45

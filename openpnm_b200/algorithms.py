@@ -24,7 +24,7 @@ from .solvers import B200PCG
 
 __all__ = ["Transport", "ReactiveTransport", "StokesFlow", "FickianDiffusion",
            "OhmicConduction", "FourierConduction", "SolutionContainer", "SteadyStateSolution",
-           "TransientReactiveTransport", "TransientFickianDiffusion",
+           "AdvectionDiffusion", "TransientReactiveTransport", "TransientFickianDiffusion",
            "TransientOhmicConduction", "TransientFourierConduction", "TransientSolution"]
 
 logger = logging.getLogger(__name__)
@@ -616,6 +616,73 @@ class ReactiveTransport(Transport):
                 self._phase[f"pore.{item}.rate"] = r
             except Exception:
                 pass
+
+
+class AdvectionDiffusion(ReactiveTransport):
+    """Advection-diffusion with an (Nt,2) conductance: non-symmetric A, solved on
+    the device by Jacobi-scaled BiCGStab (reference: AdvectionDiffusion,
+    openpnm/algorithms/_advection_diffusion.py:43-105)."""
+
+    def __init__(self, network, phase, name="ad_?", **kwargs):
+        super().__init__(network=network, phase=phase, name=name, **kwargs)
+        self.settings._update(dict(quantity="pore.concentration",
+                                   conductance="throat.ad_dif_conductance",
+                                   diffusive_conductance="throat.diffusive_conductance",
+                                   hydraulic_conductance="throat.hydraulic_conductance",
+                                   pressure="pore.pressure", cache=False))
+        self.settings._update(kwargs)
+        dict.__setitem__(self, "pore.bc.outflow", np.full(self.Np, np.nan))
+
+    def set_outflow_BC(self, pores, mode="add"):
+        """Zero-gradient outflow: stores the net hydraulic inflow of each pore as its
+        'outflow' BC value (_advection_diffusion.py:56-84)."""
+        pores = self._parse_indices(pores)
+        conns = np.asarray(self.network["throat.conns"])
+        sel = np.isin(conns[:, 0], pores) | np.isin(conns[:, 1], pores)   # find_neighbor_throats
+        C12 = conns[sel]
+        P12 = np.asarray(self._phase[self.settings["pressure"]])[C12]
+        gh = np.asarray(self._phase[self.settings["hydraulic_conductance"]])[sel]
+        Q12 = -gh * np.diff(P12, axis=1).squeeze(axis=1)
+        Qp = np.zeros(self.Np)
+        np.add.at(Qp, C12[:, 0], -Q12)
+        np.add.at(Qp, C12[:, 1], Q12)
+        self.set_BC(pores=pores, bcvalues=Qp[pores], bctype="outflow", mode=mode)
+
+    def _conductance(self):
+        g = np.asarray(self._phase[self.settings["conductance"]], dtype=np.float64)
+        if g.shape not in ((self.Nt,), (self.Nt, 2)):
+            raise Exception("Received weights are of incorrect length")
+        return g
+
+    def _assemble(self, ctx):
+        g = self._conductance()
+        if g.ndim == 1:                       # a symmetric conductance: the parent's path
+            f, nnz = super()._assemble(ctx)
+        else:
+            ctx.build_laplacian2(self._device_conns(ctx), g, self.Np)
+            self._cache_key = None
+            # the outflow step re-writes the whole diagonal (COO setdiag), so every
+            # diagonal entry is explicit in the reference's matrix
+            f, nnz = ctx.apply_bcs(self["pore.bc.value"], self["pore.bc.rate"],
+                                   keep_zero_diag=True)
+        if g.ndim == 1 and np.isfinite(self["pore.bc.outflow"]).any():
+            f, nnz = ctx.apply_bcs(self["pore.bc.value"], self["pore.bc.rate"],
+                                   keep_zero_diag=True)
+        ctx.add_to_diagonal(self["pore.bc.outflow"])
+        return f, nnz
+
+    def rate(self, pores=[], throats=[], mode="group"):
+        throats_i = self._parse_indices(throats)
+        g = self._conductance()
+        if throats_i.size and g.ndim == 2:
+            # |g[:,0] x[c1] - g[:,1] x[c0]| (_transport.py:306-319 with the flipped (Nt,2) g)
+            if self._parse_indices(pores).size:
+                raise Exception("Must specify either pores or throats, not both")
+            c = np.asarray(self.network["throat.conns"])[throats_i]
+            x = np.asarray(self.x)
+            R = np.abs(g[throats_i, 0] * x[c[:, 1]] - g[throats_i, 1] * x[c[:, 0]])
+            return np.array(np.sum(R) if mode == "group" else R, ndmin=1)
+        return super().rate(pores=pores, throats=throats, mode=mode)
 
 
 class TransientReactiveTransport(ReactiveTransport):

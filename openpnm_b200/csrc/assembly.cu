@@ -168,8 +168,9 @@ int b200_check_flags(b200_ctx* ctx) {
 // is -g[e mod Nt].  For a generic COO the triples are explicit.
 struct ConnsSrc {
   const longlong2* conns;   // (Nt) pairs
-  const double* g;
+  const double* g;          // (Nt,) symmetric weights, or (Nt,2) row-major when twoway
   int64_t Nt;
+  int twoway;               // 1: entry (c0,c1) carries g[t][0], entry (c1,c0) carries g[t][1]
 };
 
 __global__ void k_count_conns(ConnsSrc src, int64_t Np, int64_t rb, int64_t re,
@@ -178,8 +179,11 @@ __global__ void k_count_conns(ConnsSrc src, int64_t Np, int64_t rb, int64_t re,
   bool bad_idx = false, bad_val = false;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < src.Nt; t += stride) {
     longlong2 c = src.conns[t];
-    double g = src.g[t];
-    if (!isfinite(g)) bad_val = true;
+    if (src.twoway) {
+      if (!isfinite(src.g[2 * t]) || !isfinite(src.g[2 * t + 1])) bad_val = true;
+    } else if (!isfinite(src.g[t])) {
+      bad_val = true;
+    }
     if (c.x < 0 || c.x >= Np || c.y < 0 || c.y >= Np) { bad_idx = true; continue; }
     if (c.x == c.y) continue;   // self-loop: COO setdiag drops it (_coo.py:520)
     if (c.x >= rb && c.x < re) atomicAdd(&cnt[c.x - rb], 1);
@@ -208,7 +212,9 @@ __global__ void k_fill_conns(ConnsSrc src, int64_t rb, int64_t re,
     if (c.y >= rb && c.y < re) {
       int r = (int)(c.y - rb);
       int slot = atomicSub(&cursor[r], 1) - 1;
-      keys[(int64_t)rowofs[r] + slot] = ((unsigned long long)c.x << 32) | (unsigned)t;
+      // bit 31 of the low word marks the (c1 -> c0) direction of the throat
+      keys[(int64_t)rowofs[r] + slot] =
+          ((unsigned long long)c.x << 32) | (unsigned)t | 0x80000000u;
     }
   }
 }
@@ -294,13 +300,16 @@ __global__ void k_row_sort_count(const int* __restrict__ rowofs, unsigned long l
 }
 
 // Laplacian emit: off-diagonals -sum(g) per distinct neighbour (duplicates
-// added in throat order), diagonal = +sum of all incident g in (col, throat)
-// order, inserted at its sorted position.
+// added in throat order), diagonal = +column sum (scipy's in-degree Laplacian:
+// the weight of the mirrored entry), inserted at its sorted position.
+// Weights: w(t, dir) = g[t*gs + dir*gd]; symmetric (gs,gd) = (1,0), two-way
+// (Nt,2) weights (2,1).  The entry of row c0 is direction 0, of row c1 direction 1.
 __global__ void k_emit_laplacian(const int* __restrict__ rowofs,
                                  const unsigned long long* __restrict__ keys,
-                                 const double* __restrict__ g, int64_t nrows, int64_t rb,
-                                 const int* __restrict__ indptr, int* __restrict__ indices,
-                                 double* __restrict__ data, double* __restrict__ diag) {
+                                 const double* __restrict__ g, int gs, int gd, int64_t nrows,
+                                 int64_t rb, const int* __restrict__ indptr,
+                                 int* __restrict__ indices, double* __restrict__ data,
+                                 double* __restrict__ diag) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
     const int b = rowofs[r], e = rowofs[r + 1];
@@ -314,14 +323,17 @@ __global__ void k_emit_laplacian(const int* __restrict__ rowofs,
       unsigned c = (unsigned)(keys[i] >> 32);
       double s = 0.0;
       while (i < e && (unsigned)(keys[i] >> 32) == c) {
-        s += g[(unsigned)(keys[i] & 0xffffffffull)];
+        const unsigned lo = (unsigned)(keys[i] & 0xffffffffull);
+        const int64_t t = lo & 0x7fffffffu;
+        const int dir = lo >> 31;
+        s += g[t * gs + dir * gd];
+        dsum += g[t * gs + (1 - dir) * gd];
         ++i;
       }
       if (!diag_done && c > self) { dpos = o++; diag_done = true; }
       indices[o] = (int)c;
       data[o] = -s;
       ++o;
-      dsum += s;
     }
     if (!diag_done) dpos = o++;
     indices[dpos] = (int)self;
@@ -362,9 +374,9 @@ __global__ void k_emit_coo(const int* __restrict__ rowofs,
   }
 }
 
-extern "C" int b200_build_laplacian(b200_ctx* ctx, const int64_t* conns, const double* g,
-                                    int64_t Np, int64_t Nt, int64_t row_begin, int64_t row_end,
-                                    int64_t* nnz) {
+static int build_laplacian_impl(b200_ctx* ctx, const int64_t* conns, const double* g, int twoway,
+                                int64_t Np, int64_t Nt, int64_t row_begin, int64_t row_end,
+                                int64_t* nnz) {
   if (!ctx) return B200_ERR_ARG;
   if (Np <= 0 || Nt < 0 || row_begin < 0 || row_end > Np || row_begin >= row_end)
     FAIL(B200_ERR_ARG, "build_laplacian: bad sizes Np=%lld Nt=%lld rows=[%lld,%lld)",
@@ -391,7 +403,7 @@ extern "C" int b200_build_laplacian(b200_ctx* ctx, const int64_t* conns, const d
   int* cur = ctx->w_tmp1.as<int>();
   CK(cudaMemsetAsync(cnt, 0, (size_t)(nr + 1) * sizeof(int), ctx->stream));
 
-  ConnsSrc src{reinterpret_cast<const longlong2*>(conns), g, Nt};
+  ConnsSrc src{reinterpret_cast<const longlong2*>(conns), g, Nt, twoway};
   const int B = 256;
   LAUNCH(ctx, k_count_conns, grid_for(Nt, B), B, 0, src, Np, row_begin, row_end, cnt, flags);
   CK(cudaMemcpyAsync(cur, cnt, (size_t)nr * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -410,15 +422,60 @@ extern "C" int b200_build_laplacian(b200_ctx* ctx, const int64_t* conns, const d
   CK(ctx->pure_indices.ensure((size_t)total * sizeof(int)));
   CK(ctx->pure_data.ensure((size_t)total * sizeof(double)));
   CK(ctx->pure_diag.ensure((size_t)nr * sizeof(double)));
-  LAUNCH(ctx, k_emit_laplacian, grid_for(nr, 128), 128, 0, rowofs, keys, g, nr, row_begin,
-         ctx->pure_indptr.as<int>(), ctx->pure_indices.as<int>(), ctx->pure_data.as<double>(),
-         ctx->pure_diag.as<double>());
+  LAUNCH(ctx, k_emit_laplacian, grid_for(nr, 128), 128, 0, rowofs, keys, g, twoway ? 2 : 1,
+         twoway ? 1 : 0, nr, row_begin, ctx->pure_indptr.as<int>(), ctx->pure_indices.as<int>(),
+         ctx->pure_data.as<double>(), ctx->pure_diag.as<double>());
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->pure_nnz = total;
   ctx->have_pure = true;
   ctx->f_override = false;
+  ctx->nonsym = twoway != 0;
   if (nnz) *nnz = total;
+  return B200_OK;
+}
+
+extern "C" int b200_build_laplacian(b200_ctx* ctx, const int64_t* conns, const double* g,
+                                    int64_t Np, int64_t Nt, int64_t row_begin, int64_t row_end,
+                                    int64_t* nnz) {
+  return build_laplacian_impl(ctx, conns, g, 0, Np, Nt, row_begin, row_end, nnz);
+}
+
+extern "C" int b200_build_laplacian2(b200_ctx* ctx, const int64_t* conns, const double* g2,
+                                     int64_t Np, int64_t Nt, int64_t* nnz) {
+  return build_laplacian_impl(ctx, conns, g2, 1, Np, Nt, 0, Np, nnz);
+}
+
+// diag[i] += add[i] where add is finite (AdvectionDiffusion outflow BC,
+// openpnm/algorithms/_advection_diffusion.py:86-105); the diagonal entry of the
+// system CSR is patched, so apply_bcs must have kept every diagonal entry
+__global__ void k_add_diag(const double* __restrict__ add, int64_t n, int64_t rb,
+                           double* __restrict__ diag, const int* __restrict__ diagpos,
+                           double* __restrict__ data, int* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double a = add[i + rb];
+    if (isnan(a)) continue;
+    if (!isfinite(a)) { flags[FLAG_NONFINITE] = 1; continue; }
+    const double d = diag[i] + a;
+    diag[i] = d;
+    const int dp = diagpos[i];
+    if (dp >= 0) data[dp] = d; else flags[FLAG_ZERO_DIAG] = 1;
+  }
+}
+
+extern "C" int b200_add_to_diagonal(b200_ctx* ctx, const double* add) {
+  if (!ctx || !ctx->have_sys || !add) return B200_ERR_ARG;
+  RET(b200_zero_flags(ctx));
+  LAUNCH(ctx, k_add_diag, grid_for(ctx->n, 256), 256, 0, add, ctx->n, ctx->row_begin,
+         ctx->sys_diag.as<double>(), ctx->sys_diagpos.as<int>(), ctx->sys_data.as<double>(),
+         ctx->w_flags.as<int>());
+  CK(cudaGetLastError());
+  RET(b200_check_flags(ctx));
+  if (ctx->flags_h[FLAG_ZERO_DIAG])
+    FAIL(B200_ERR_ARG, "add_to_diagonal: a diagonal entry is missing (apply_bcs with keep_zero_diag)");
+  ctx->lin_valid = false;
+  ctx->sys_epoch++;
   return B200_OK;
 }
 
@@ -476,6 +533,7 @@ extern "C" int b200_load_coo(b200_ctx* ctx, const int32_t* row, const int32_t* c
   ctx->sys_nnz = total;
   ctx->have_sys = true;
   ctx->sys_generic = true;
+  ctx->nonsym = false;
   ctx->sys_epoch++;
   if (nnz) *nnz = total;
   return B200_OK;
@@ -525,6 +583,7 @@ extern "C" int b200_load_csr(b200_ctx* ctx, const int32_t* indptr, const int32_t
   ctx->sys_nnz = nnz;
   ctx->have_sys = true;
   ctx->sys_generic = true;
+  ctx->nonsym = false;
   ctx->lin_valid = false;
   ctx->sys_epoch++;
   return B200_OK;

@@ -107,6 +107,7 @@ struct b200_ctx {
   DevBuf pure_indptr, pure_indices, pure_data, pure_diag;
   int64_t pure_nnz = 0;
   bool have_pure = false;
+  bool nonsym = false;        // two-way (Nt,2) weights: A is not symmetric -> BiCGStab, no DIA-sym
 
   // system matrix (after BCs, or loaded), b, diagonal bookkeeping
   DevBuf sys_indptr, sys_indices, sys_data, sys_diag, sys_diagpos, b;
@@ -136,6 +137,7 @@ struct b200_ctx {
   DevBuf o_indptr, o_cols, o_vals, o_rowstart;  // scaled off-diagonal CSR
   int64_t o_nnz = 0, o_nblocks = 0, o_maxrow = 0;
   DevBuf vx, vr, vp, vap, vb;  // PCG vectors (padded layout)
+  DevBuf vbi;                  // BiCGStab extras: rhat, s (padded), t
   DevBuf scal;                 // SC_COUNT doubles
   double* scal_h = nullptr;    // pinned mirror
 
@@ -257,6 +259,16 @@ int b200_halo_exchange_end(b200_ctx* ctx);                     // stream waits f
 int b200_allreduce_sum(b200_ctx* ctx, double* dev, int count); // in place, fp64
 int b200_allreduce_max_host(b200_ctx* ctx, int64_t* v);
 void b200_comm_release(b200_ctx* ctx);
+// solver.cu helpers used by transient.cu / bicgstab.cu
+int b200_spmv_dots(b200_ctx* ctx, const double* w_owned, const double* rv_owned,
+                   double* out_owned, double* group);
+int b200_launch_init(b200_ctx* ctx, const double* x0, double* xt, double* bt, double* out_b2);
+int b200_launch_resid(b200_ctx* ctx, const double* bt, const double* ap, const double* d,
+                      double* r, double* p, double* out_rr, double* out_true);
+int b200_launch_final(b200_ctx* ctx, const double* xt, double* x);
+const double* b200_cur_diag(b200_ctx* ctx);
+int b200_bicgstab(b200_ctx* ctx, const double* x0, double rtol, double atol, int64_t maxiter,
+                  double* x, int64_t* iters, double* relres, int* info);
 // p2p.cu
 void b200_p2p_release(b200_ctx* ctx);
 bool b200_p2p_usable(b200_ctx* ctx);

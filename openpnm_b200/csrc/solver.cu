@@ -406,7 +406,7 @@ static int prepare_operator(b200_ctx* ctx) {
   const int64_t upper = (ctx->sys_nnz - n) / 2;   // off-diagonals are symmetric pairs
   bool want_dia = !tab.overflow && tab.n > 0 &&
                   (double)upper >= 0.25 * (double)tab.n * (double)n;
-  if (ctx->force_fmt == B200_FMT_CSR) want_dia = false;
+  if (ctx->force_fmt == B200_FMT_CSR || ctx->nonsym) want_dia = false;
   if (ctx->force_fmt == B200_FMT_DIA && (tab.overflow || tab.n == 0))
     FAIL(B200_ERR_ARG, "DIA format forced but the matrix has more than %d diagonals",
          B200_MAX_DIAGS);
@@ -777,6 +777,29 @@ __global__ void k_fill_const(double* a, int64_t n, double v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] = v;
 }
 
+// launch helpers shared with bicgstab.cu
+int b200_launch_init(b200_ctx* ctx, const double* x0, double* xt, double* bt, double* out_b2) {
+  const int g1 = grid_for(ctx->n, PCG_T);
+  LAUNCH(ctx, k_pcg_init, g1, PCG_T, 0, x0, cur_b(ctx), owned(ctx->sc, ctx->pad),
+         ctx->sys_indptr.as<int>(), ctx->sys_diagpos.as<int>(), ctx->unit_diag ? 1 : 0,
+         ctx->dexp.as<double>(), xt, bt, ctx->n, ctx->w_part.as<double>(),
+         ctx->w_ticket.as<unsigned>(), out_b2, ctx->w_flags.as<int>());
+  return B200_OK;
+}
+int b200_launch_resid(b200_ctx* ctx, const double* bt, const double* ap, const double* d,
+                      double* r, double* p, double* out_rr, double* out_true) {
+  const int g1 = grid_for(ctx->n, PCG_T);
+  LAUNCH(ctx, k_pcg_resid, g1, PCG_T, 0, bt, ap, d, r, p, ctx->n, ctx->w_part.as<double>(),
+         ctx->w_ticket.as<unsigned>(), out_rr, out_true);
+  return B200_OK;
+}
+int b200_launch_final(b200_ctx* ctx, const double* xt, double* x) {
+  LAUNCH(ctx, k_pcg_final, grid_for(ctx->n, PCG_T), PCG_T, 0, xt, owned(ctx->sc, ctx->pad), x,
+         ctx->n);
+  return B200_OK;
+}
+const double* b200_cur_diag(b200_ctx* ctx) { return cur_diag(ctx); }
+
 // --------------------------------------------------------------- launchers
 static int pcg_grid(b200_ctx* ctx, int per_thread) {
   // persistent-style grid: a multiple of the SM count, grid-stride inside
@@ -851,6 +874,13 @@ static int launch_spmv_dot(b200_ctx* ctx, const double* p_owned, const double* r
 
 // out = A~ w on the prepared operator (w, out: owned pointers of padded vectors);
 // the dot products K_A makes on the side land in a scratch group
+// K_A on arbitrary operands: out = A~ w and the three sums w.out, rv.out, out.out
+// into group[G_PAP], group[G_RAP], group[G_APAP]
+int b200_spmv_dots(b200_ctx* ctx, const double* w_owned, const double* rv_owned,
+                   double* out_owned, double* group) {
+  return launch_spmv_dot(ctx, w_owned, rv_owned, out_owned, group);
+}
+
 int b200_apply_operator(b200_ctx* ctx, const double* w_owned, double* out_owned) {
   return launch_spmv_dot(ctx, w_owned, ctx->vr.as<double>() + ctx->pad, out_owned,
                          ctx->scal.as<double>() + SC_AUX0);
@@ -863,6 +893,7 @@ extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double ato
     return B200_ERR_ARG;
   }
   CK(cudaSetDevice(ctx->device));
+  if (ctx->nonsym) return b200_bicgstab(ctx, x0, rtol, atol, maxiter, x, iters, relres, info);
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   RET(b200_pcg_prepare(ctx, ctx->force_fmt));
   CK(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -103,6 +103,27 @@ class Context:
         self.row_begin = int(row_begin)
         return nnz.value
 
+    def build_laplacian2(self, conns, g2, Np):
+        """(Nt,2) weights -> non-symmetric Laplacian (AdvectionDiffusion)."""
+        torch = _torch()
+        conns = self.to_device(conns, torch.int64)
+        g2 = self.to_device(np.ascontiguousarray(g2, dtype=np.float64), torch.float64)
+        Nt = int(g2.numel() // 2)
+        if conns.numel() != 2 * Nt:
+            raise ValueError("conns must be (Nt, 2) and g2 (Nt, 2)")
+        nnz = C.c_int64()
+        self._ck(self.lib.b200_build_laplacian2(self._h, self._p(conns), self._p(g2), int(Np), Nt,
+                                                C.byref(nnz)))
+        self._keep["conns"], self._keep["g"] = conns, g2
+        self.n = int(Np)
+        self.row_begin = 0
+        return nnz.value
+
+    def add_to_diagonal(self, add):
+        torch = _torch()
+        add = self.to_device(add, torch.float64)
+        self._ck(self.lib.b200_add_to_diagonal(self._h, self._p(add)))
+
     def check_topology(self, conns, Np, bc_value=None, bc_rate=None):
         """(number of clusters, number of clusters without any BC pore)"""
         torch = _torch()

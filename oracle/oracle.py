@@ -31,6 +31,7 @@ __all__ = [
     "cubic_network", "adjacency_coo", "laplacian_coo", "build_A", "apply_bcs",
     "apply_sources", "to_csr", "source_term", "picard_run", "rate",
     "jacobi_pcg", "spsolve", "transport_run", "delaunay_network", "transient_run",
+    "apply_outflow", "outflow_values",
 ]
 
 
@@ -88,15 +89,18 @@ def delaunay_network(points):
 # assembly
 # --------------------------------------------------------------------------
 def adjacency_coo(conns, g, Np):
-    """`Network.create_adjacency_matrix(weights=g, fmt='coo')`, symmetric branch.
+    """`Network.create_adjacency_matrix(weights=g, fmt='coo')`.
 
-    openpnm/network/_network.py:274-293: row=[c0;c1], col=[c1;c0], data=[g;g].
+    openpnm/network/_network.py:274-293: row=[c0;c1], col=[c1;c0]; an (Nt,)
+    weight gives data=[g;g] (symmetric), an (Nt,2) weight gives
+    data=weights.flatten(order='F') = [g[:,0]; g[:,1]] (:281-285), i.e. entry
+    (c0,c1) carries g[:,0] and entry (c1,c0) carries g[:,1] (AdvectionDiffusion).
     """
     conns = np.asarray(conns)
     g = np.asarray(g, dtype=float)
     row = np.append(conns[:, 0], conns[:, 1])
     col = np.append(conns[:, 1], conns[:, 0])
-    data = np.append(g, g)
+    data = g.flatten(order="F") if g.ndim == 2 else np.append(g, g)
     return row, col, data
 
 
@@ -170,6 +174,33 @@ def apply_bcs(A, Np, bc_value=None, bc_rate=None):
         nz = data != 0
         row, col, data = row[nz], col[nz], data[nz]
     return (row, col, data), b, f
+
+
+def apply_outflow(A, Np, bc_outflow):
+    """`AdvectionDiffusion._apply_BCs`, the part after the parent's
+    (openpnm/algorithms/_advection_diffusion.py:86-105): diag[ind] += outflow[ind]
+    through COO `setdiag` (all Np diagonal entries become explicit)."""
+    row, col, data = A
+    diag = _coo_diagonal(row, col, data, Np)
+    ind = np.isfinite(bc_outflow)
+    diag[ind] += bc_outflow[ind]
+    return _coo_setdiag(row, col, data, diag)
+
+
+def outflow_values(conns, gh, pressure, pores, Np):
+    """`AdvectionDiffusion.set_outflow_BC` (_advection_diffusion.py:56-84): the net
+    hydraulic flow rate into each listed pore, stored as its 'outflow' BC value."""
+    conns = np.asarray(conns)
+    sel = np.isin(conns[:, 0], pores) | np.isin(conns[:, 1], pores)
+    C12 = conns[sel]
+    P12 = np.asarray(pressure)[C12]
+    Q12 = -np.asarray(gh)[sel] * np.diff(P12, axis=1).squeeze(axis=1)
+    Qp = np.zeros(Np)
+    np.add.at(Qp, C12[:, 0], -Q12)
+    np.add.at(Qp, C12[:, 1], Q12)
+    out = np.full(Np, np.nan)
+    out[pores] = Qp[pores]
+    return out
 
 
 def apply_sources(A, b, Np, sources):
@@ -283,7 +314,7 @@ def _termination_check(state, f, x, dx, f_rtol, x_rtol):
 
 def picard_run(conns, g, Np, bc_value=None, bc_rate=None, sources=(), x0=None,
                solver=None, relaxation_factor=1.0, newton_maxiter=5000,
-               f_rtol=1e-6, x_rtol=1e-6):
+               f_rtol=1e-6, x_rtol=1e-6, bc_outflow=None):
     """`Transport.run` + `ReactiveTransport._run_special` for one algorithm.
 
     _transport.py:171-221 and _reactive_transport.py:150-213, including the
@@ -303,6 +334,8 @@ def picard_run(conns, g, Np, bc_value=None, bc_rate=None, sources=(), x0=None,
 
     def update(x):
         A, b, _ = apply_bcs(pure, Np, bc_value, bc_rate)
+        if bc_outflow is not None:
+            A = apply_outflow(A, Np, bc_outflow)
         lin = []
         for mask, kind, params in sources:
             S1, S2, _ = source_term(kind, x, params)

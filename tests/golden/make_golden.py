@@ -422,6 +422,78 @@ def g13_transient():
     print("g13", META["g13_transient_4x3x1"], META["g13_transient_8x7x6_power_law"])
 
 
+def g14_advection_diffusion():
+    # tests/unit/algorithms/AdvectionDiffusionTest.py:10-115 (4x3x1, powerlaw / upwind)
+    mod = op.models.physics.ad_dif_conductance.ad_dif
+
+    def make(shape, gh, gd, schemes, outflow_label=None, seed=None):
+        pn = op.network.Cubic(shape=shape, spacing=1.0)
+        pn["throat.length"] = 1.0 if seed is None else np.random.default_rng(seed).uniform(
+            0.5, 1.5, pn.Nt)
+        ph = op.phase.Phase(network=pn)
+        ph["throat.diffusive_conductance"] = gd(pn) if callable(gd) else gd
+        ph["throat.hydraulic_conductance"] = gh(pn) if callable(gh) else gh
+        sf = op.algorithms.StokesFlow(network=pn, phase=ph)
+        sf.set_value_BC(pores=pn.pores("right"), values=1)
+        sf.set_value_BC(pores=pn.pores("left"), values=0)
+        sf.run(solver=op.solvers.ScipySpsolve())
+        ph.update(sf.soln)
+        out = {}
+        for sch in schemes:
+            ph.add_model(propname=f"throat.ad_{sch}", model=mod, s_scheme=sch)
+            ph.regenerate_models()
+            ad = op.algorithms.AdvectionDiffusion(network=pn, phase=ph)
+            ad.settings["conductance"] = f"throat.ad_{sch}"
+            ad.set_value_BC(pores=pn.pores("right"), values=2)
+            if outflow_label is None:
+                ad.set_value_BC(pores=pn.pores("left"), values=0)
+            else:
+                ad.set_outflow_BC(pores=pn.pores(outflow_label))
+                # a second Dirichlet patch so the field is not trivially uniform
+                taken = np.union1d(pn.pores("right"), pn.pores(outflow_label))
+                ad.set_value_BC(pores=np.setdiff1d(pn.pores("top"), taken)[::2], values=0.3)
+            ad.run(solver=op.solvers.ScipySpsolve())
+            g2 = np.array(ph[f"throat.ad_{sch}"], dtype=float)
+            bcv = np.array(ad["pore.bc.value"], dtype=float)
+            bco = np.array(ad["pore.bc.outflow"], dtype=float)
+            # oracle cross-check: assembly bit-exact, outflow values, solution
+            if outflow_label is not None:
+                ov = oracle.outflow_values(pn["throat.conns"], ph["throat.hydraulic_conductance"],
+                                           ph["pore.pressure"], pn.pores(outflow_label), pn.Np)
+                assert np.allclose(ov[np.isfinite(ov)], bco[np.isfinite(bco)], rtol=1e-12)
+            res = oracle.picard_run(pn["throat.conns"], g2, pn.Np, bc_value=bcv,
+                                    bc_rate=np.array(ad["pore.bc.rate"], dtype=float),
+                                    bc_outflow=bco)
+            Ao, Ar = oracle.to_csr(res["A"], pn.Np), csr_of(ad)
+            assert np.array_equal(Ao.indptr, Ar.indptr) and np.array_equal(Ao.indices, Ar.indices)
+            assert np.allclose(Ao.data, Ar.data, rtol=1e-13, atol=0)
+            assert np.allclose(res["x"], ad.x, rtol=1e-9, atol=1e-12)
+            assert res["num_iter"] == ad.soln.num_iter
+            out[sch] = dict(g2=g2, bc_value=bcv, bc_outflow=bco, x=np.array(ad.x),
+                            indptr=Ar.indptr.astype(np.int32), indices=Ar.indices.astype(np.int32),
+                            data=Ar.data, b=np.array(ad.b))
+        return pn, ph, out
+
+    pn, ph, out = make([4, 3, 1], 1e-15, 1e-15, ["powerlaw", "upwind"])
+    assert np.allclose(out["powerlaw"]["x"][3:9],
+                       [0.89653] * 3 + [1.53924] * 3, rtol=1e-5)
+    assert np.allclose(out["upwind"]["x"][3:9], [0.86486] * 3 + [1.51351] * 3, rtol=1e-5)
+    for sch, d in out.items():
+        save(f"g14_ad_4x3x1_{sch}", conns=pn["throat.conns"].astype(np.int64), **d)
+    # heterogeneous 3-D case with an outflow boundary
+    pn, ph, out = make([9, 7, 5],
+                       lambda pn: 10.0 ** np.random.default_rng(1).uniform(-15, -14, pn.Nt),
+                       lambda pn: 10.0 ** np.random.default_rng(2).uniform(-15.5, -14.5, pn.Nt),
+                       ["powerlaw", "hybrid"], outflow_label="left", seed=3)
+    for sch, d in out.items():
+        save(f"g14_ad_9x7x5_outflow_{sch}", conns=pn["throat.conns"].astype(np.int64),
+             gh=np.array(ph["throat.hydraulic_conductance"]),
+             pressure=np.array(ph["pore.pressure"]), left=pn.pores("left").astype(np.int64), **d)
+    META["g14_ad"] = dict(cases=["g14_ad_4x3x1_powerlaw", "g14_ad_4x3x1_upwind",
+                                 "g14_ad_9x7x5_outflow_powerlaw", "g14_ad_9x7x5_outflow_hybrid"])
+    print("g14 ok", {k: float(v["x"].mean()) for k, v in out.items()})
+
+
 def g8_big():
     # config 1 scale: Cubic 50^3, SuperLU (~3 min)
     n = 50
@@ -443,7 +515,7 @@ if __name__ == "__main__":
     if os.path.exists(meta_path):
         META.update(json.load(open(meta_path)))
     cases = [g1_solvers, g2_stokes, g3_reactive, g4_csr, g5_conduit, g6_profiles,
-             g7_hetero, g11_irregular, g13_transient]
+             g7_hetero, g11_irregular, g13_transient, g14_advection_diffusion]
     if args.big:
         cases = [g8_big]
     for fn in cases:

@@ -144,3 +144,26 @@ def test_transient_oracle_against_reference(golden, golden_meta):
                                 rtol=m["rtol"], atol=m["atol"])
     assert np.array_equal(t, g["t"])
     np.testing.assert_allclose(Y, g["Y"], rtol=1e-10, atol=0)
+
+
+AD_CASES = ["g14_ad_4x3x1_powerlaw", "g14_ad_4x3x1_upwind", "g14_ad_9x7x5_outflow_powerlaw",
+            "g14_ad_9x7x5_outflow_hybrid"]
+
+
+@pytest.mark.parametrize("name", AD_CASES)
+def test_advection_diffusion_oracle(name, golden):
+    """AdvectionDiffusionTest.py:10-115 and heterogeneous cases with an outflow BC."""
+    g = golden(name)
+    Np = g["x"].size
+    res = oracle.picard_run(g["conns"], g["g2"], Np, bc_value=g["bc_value"], bc_outflow=g["bc_outflow"])
+    M = oracle.to_csr(res["A"], Np)
+    assert np.array_equal(M.indptr, g["indptr"]) and np.array_equal(M.indices, g["indices"])
+    np.testing.assert_allclose(M.data, g["data"], rtol=1e-13, atol=0)
+    np.testing.assert_allclose(res["x"], g["x"], rtol=1e-9, atol=1e-12)
+    assert (abs(M - M.T) > 0).nnz > 0                      # genuinely non-symmetric
+    if "left" in g:
+        ov = oracle.outflow_values(g["conns"], g["gh"], g["pressure"], g["left"], Np)
+        m = np.isfinite(g["bc_outflow"])
+        np.testing.assert_allclose(ov[m], g["bc_outflow"][m], rtol=1e-12)
+    if name == "g14_ad_4x3x1_powerlaw":
+        np.testing.assert_allclose(g["x"][3:9], [0.89653] * 3 + [1.53924] * 3, rtol=1e-5)
