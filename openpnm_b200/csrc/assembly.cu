@@ -490,6 +490,44 @@ static int alloc_system(b200_ctx* ctx, int64_t n, int64_t nnz) {
   return B200_OK;
 }
 
+// every off-diagonal entry must have an equal mirror entry, else the system is
+// flagged non-symmetric (-> BiCGStab instead of CG); binary search in the
+// column-sorted mirror row
+__global__ void k_check_symmetric(const int* __restrict__ indptr, const int* __restrict__ indices,
+                                  const double* __restrict__ data, int64_t n,
+                                  int* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    for (int e = indptr[r]; e < indptr[r + 1]; ++e) {
+      const int j = indices[e];
+      if ((int64_t)j == r) continue;
+      int lo = indptr[j], hi = indptr[j + 1];
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)indices[mid] < r) lo = mid + 1; else hi = mid;
+      }
+      const double a = data[e];
+      if (lo >= indptr[j + 1] || (int64_t)indices[lo] != r) {
+        if (a != 0.0) bad = true;
+      } else {
+        const double b = data[lo];
+        if (fabs(a - b) > 1e-12 * fmax(fabs(a), fabs(b))) bad = true;
+      }
+    }
+  }
+  if (bad) flags[FLAG_NONSYM] = 1;
+}
+
+static int detect_nonsymmetric(b200_ctx* ctx) {
+  RET(b200_zero_flags(ctx));
+  LAUNCH(ctx, k_check_symmetric, grid_for(ctx->n, 128), 128, 0, ctx->sys_indptr.as<int>(),
+         ctx->sys_indices.as<int>(), ctx->sys_data.as<double>(), ctx->n, ctx->w_flags.as<int>());
+  RET(b200_check_flags(ctx));
+  ctx->nonsym = ctx->flags_h[FLAG_NONSYM] != 0;
+  return B200_OK;
+}
+
 extern "C" int b200_load_coo(b200_ctx* ctx, const int32_t* row, const int32_t* col,
                              const double* data, int64_t nnz_in, int64_t n, int64_t* nnz) {
   if (!ctx) return B200_ERR_ARG;
@@ -533,8 +571,8 @@ extern "C" int b200_load_coo(b200_ctx* ctx, const int32_t* row, const int32_t* c
   ctx->sys_nnz = total;
   ctx->have_sys = true;
   ctx->sys_generic = true;
-  ctx->nonsym = false;
   ctx->sys_epoch++;
+  RET(detect_nonsymmetric(ctx));
   if (nnz) *nnz = total;
   return B200_OK;
 }
@@ -583,10 +621,9 @@ extern "C" int b200_load_csr(b200_ctx* ctx, const int32_t* indptr, const int32_t
   ctx->sys_nnz = nnz;
   ctx->have_sys = true;
   ctx->sys_generic = true;
-  ctx->nonsym = false;
   ctx->lin_valid = false;
   ctx->sys_epoch++;
-  return B200_OK;
+  return detect_nonsymmetric(ctx);
 }
 
 extern "C" int b200_set_b(b200_ctx* ctx, const double* b) {

@@ -88,3 +88,17 @@ def test_advection_diffusion_medium_vs_direct(b2):
     M = oracle.to_csr(ref["A"], pn.Np)
     A = ad.A
     assert np.array_equal(A.indptr, M.indptr) and np.array_equal(A.indices, M.indices)
+
+
+def test_b200pcg_solve_on_nonsymmetric_coo(b2, golden):
+    """The drop-in solver detects a non-symmetric A (the reference's AdvectionDiffusion
+    hands one to solver.solve) and switches from CG to BiCGStab."""
+    import scipy.sparse as sprs
+    g = golden("g14_ad_9x7x5_outflow_powerlaw")
+    Np = g["x"].size
+    A = sprs.csr_matrix((g["data"], g["indices"], g["indptr"]), shape=(Np, Np))
+    s = b2.B200PCG(tol=1e-13)
+    x, code = s.solve(A=A.tocoo(), b=g["b"], x0=np.zeros(Np))
+    assert code == 0
+    assert np.max(np.abs(x - g["x"])) <= 1e-8 * np.max(np.abs(g["x"]))
+    assert s.info["fmt"] == "csr"

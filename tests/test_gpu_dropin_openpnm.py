@@ -123,3 +123,27 @@ def test_b200_algorithms_accept_reference_objects(op, b2):
     A = alg.A
     assert np.array_equal(A.indptr, A_ref.indptr) and np.array_equal(A.indices, A_ref.indices)
     np.testing.assert_allclose(A.data, A_ref.data, rtol=1e-7, atol=0)
+
+
+def test_reference_advection_diffusion_with_b200(op, b2):
+    """The reference's own AdvectionDiffusion (AdvectionDiffusionTest.py:10-93) solved
+    with the B200 solver object: non-symmetric A -> BiCGStab behind the same API."""
+    pn = op.network.Cubic(shape=[4, 3, 1], spacing=1.0)
+    pn["throat.length"] = 1.0
+    ph = op.phase.Phase(network=pn)
+    ph["throat.diffusive_conductance"] = 1e-15
+    ph["throat.hydraulic_conductance"] = 1e-15
+    sf = op.algorithms.StokesFlow(network=pn, phase=ph)
+    sf.set_value_BC(pores=pn.pores("right"), values=1)
+    sf.set_value_BC(pores=pn.pores("left"), values=0)
+    sf.run(solver=b2.B200PCG(tol=1e-13))
+    ph.update(sf.soln)
+    ad = op.algorithms.AdvectionDiffusion(network=pn, phase=ph)
+    ad.set_value_BC(pores=pn.pores("right"), values=2)
+    ad.set_value_BC(pores=pn.pores("left"), values=0)
+    ph.add_model(propname="throat.ad_dif_conductance",
+                 model=op.models.physics.ad_dif_conductance.ad_dif, s_scheme="powerlaw")
+    ad.run(solver=b2.B200PCG(tol=1e-13))
+    x = [0., 0., 0., 0.89653, 0.89653, 0.89653, 1.53924, 1.53924, 1.53924, 2., 2., 2.]
+    np.testing.assert_allclose(ad["pore.concentration"], x, rtol=1e-5, atol=1e-12)
+    assert ad.soln.is_converged
