@@ -25,7 +25,8 @@ from .solvers import B200PCG
 __all__ = ["Transport", "ReactiveTransport", "StokesFlow", "FickianDiffusion",
            "OhmicConduction", "FourierConduction", "SolutionContainer", "SteadyStateSolution",
            "AdvectionDiffusion", "TransientReactiveTransport", "TransientFickianDiffusion",
-           "TransientOhmicConduction", "TransientFourierConduction", "TransientSolution"]
+           "TransientOhmicConduction", "TransientFourierConduction",
+           "TransientAdvectionDiffusion", "TransientSolution"]
 
 logger = logging.getLogger(__name__)
 
@@ -776,6 +777,14 @@ class TransientFourierConduction(TransientReactiveTransport):
         self.settings._update(dict(quantity="pore.temperature",
                                    conductance="throat.thermal_conductance"))
         self.settings._update(kwargs)
+
+
+class TransientAdvectionDiffusion(TransientReactiveTransport, AdvectionDiffusion):
+    """_transient_advection_diffusion.py: the transient driver on the
+    non-symmetric AdvectionDiffusion assembly."""
+
+    def __init__(self, network, phase, name="trans_ad_?", **kwargs):
+        super().__init__(network=network, phase=phase, name=name, **kwargs)
 
 
 class StokesFlow(ReactiveTransport):

@@ -384,7 +384,7 @@ def transport_run(conns, g, Np, bc_value=None, bc_rate=None, solver=None, x0=Non
 
 
 def transient_run(conns, g, Np, volume, x0, tspan, saveat=None, bc_value=None, bc_rate=None,
-                  sources=(), rtol=1e-6, atol=1e-6):
+                  sources=(), rtol=1e-6, atol=1e-6, bc_outflow=None):
     """`TransientReactiveTransport.run` with `ScipyRK45`
     (openpnm/algorithms/_transient_reactive_transport.py:51-123,
     openpnm/integrators/_scipy.py:18-56): dy/dt = (-A y + b) / V with A, b
@@ -405,6 +405,8 @@ def transient_run(conns, g, Np, volume, x0, tspan, saveat=None, bc_value=None, b
 
     def ode_func(t, y):
         A, b, _ = apply_bcs(pure, Np, bc_value, bc_rate)
+        if bc_outflow is not None:
+            A = apply_outflow(A, Np, bc_outflow)
         lin = [(mask, *source_term(kind, y, params)[:2]) for mask, kind, params in sources]
         if lin:
             A, b = apply_sources(A, b, Np, lin)

@@ -102,3 +102,28 @@ def test_b200pcg_solve_on_nonsymmetric_coo(b2, golden):
     assert code == 0
     assert np.max(np.abs(x - g["x"])) <= 1e-8 * np.max(np.abs(g["x"]))
     assert s.info["fmt"] == "csr"
+
+
+def test_transient_advection_diffusion_vs_oracle(b2):
+    """TransientAdvectionDiffusion = the RK45 driver on the non-symmetric assembly."""
+    shape = (12, 6, 5)
+    pn = b2.Cubic(shape, spacing=1e-4)
+    rng = np.random.default_rng(4)
+    gd = 10.0 ** rng.uniform(-15.5, -14.5, pn.Nt)
+    Q = rng.normal(0, 3e-15, pn.Nt)
+    g2 = np.column_stack((np.maximum(-Q, 0) + gd, np.maximum(Q, 0) + gd))
+    V = rng.uniform(0.5, 1.5, pn.Np) * 1e-13
+    pn["pore.volume"] = V
+    ph = b2.Phase(pn)
+    dict.__setitem__(ph, "throat.ad_dif_conductance", g2)
+    alg = b2.algorithms.TransientAdvectionDiffusion(network=pn, phase=ph)
+    alg.set_value_BC(pores=pn.pores("right"), values=2.0)
+    alg.set_value_BC(pores=pn.pores("left"), values=0.0)
+    saveat = np.array([0.0, 1.0, 4.0, 10.0])
+    alg.run(x0=0.5, tspan=(0, 10.0), saveat=saveat, integrator=b2.B200RK45(atol=1e-9, rtol=1e-8))
+    sol = alg.soln["pore.concentration"]
+    t_o, Y_o = oracle.transient_run(pn.conns, g2, pn.Np, V, 0.5, (0, 10.0), saveat=saveat,
+                                    bc_value=alg["pore.bc.value"],
+                                    bc_outflow=alg["pore.bc.outflow"], rtol=1e-8, atol=1e-9)
+    assert np.array_equal(sol.t, t_o)
+    assert np.max(np.abs(np.asarray(sol) - Y_o)) <= 1e-8 * np.max(np.abs(Y_o))
