@@ -123,16 +123,18 @@ def reference_openpnm_sample(n, rtol=RTOL):
     imported through tests/ref_shim.py): `StokesFlow.run(solver=ScipyCG(tol))` + `rate()`
     on a Cubic n^3 sample -- its own assembly (x3), topology check and SciPy CG.
     Returns None when the reference cannot be imported."""
+    import contextlib
+    import logging
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    logging.disable(logging.CRITICAL)      # the reference logs through rich, to stdout
     try:
-        import ref_shim
-        op = ref_shim.import_reference()
+        with contextlib.redirect_stdout(sys.stderr):   # stdout carries the one JSON line only
+            import ref_shim
+            op = ref_shim.import_reference()
     except Exception:
         op = None
     if op is None:
         return None
-    import logging
-    logging.disable(logging.CRITICAL)
     pn = op.network.Cubic(shape=[n, n, n], spacing=1e-4)
     ph = op.phase.Phase(network=pn)
     ph["throat.hydraulic_conductance"] = conductance(pn.Nt)
