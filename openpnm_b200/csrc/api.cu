@@ -48,7 +48,8 @@ extern "C" int b200_destroy(b200_ctx* ctx) {
                     &ctx->dia_store, &ctx->o_indptr, &ctx->o_cols, &ctx->o_vals, &ctx->o_rowstart,
                     &ctx->vx, &ctx->vr, &ctx->vp, &ctx->vap, &ctx->vb, &ctx->scal, &ctx->w_cnt,
                     &ctx->w_keys, &ctx->w_scan, &ctx->w_part, &ctx->w_ticket, &ctx->w_flags,
-                    &ctx->w_tmp0, &ctx->w_tmp1, &ctx->w_tmp2})
+                    &ctx->w_tmp0, &ctx->w_tmp1, &ctx->w_tmp2, &ctx->vbi, &ctx->h_row, &ctx->h_col,
+                    &ctx->h_dat, &ctx->h_vec})
     b->release();
   if (ctx->scal_h) cudaFreeHost(ctx->scal_h);
   if (ctx->flags_h) cudaFreeHost(ctx->flags_h);
@@ -99,15 +100,18 @@ extern "C" int b200_solve_coo_h(b200_ctx* ctx, const int32_t* row_h, const int32
   if (!ctx || !row_h || !col_h || !data_h || !b_h || !x_h || n <= 0 || nnz_in < 0)
     return B200_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  DevBuf drow, dcol, ddat, dvec;
+  // staging buffers live in the context: a Picard loop of the reference calls
+  // this thousands of times with the same sizes (_reactive_transport.py:196-210)
+  DevBuf& drow = ctx->h_row;
+  DevBuf& dcol = ctx->h_col;
+  DevBuf& ddat = ctx->h_dat;
+  DevBuf& dvec = ctx->h_vec;
   int rc = B200_OK;
-  auto cleanup = [&]() { drow.release(); dcol.release(); ddat.release(); dvec.release(); };
 #define CKX(call)                                                           \
   do {                                                                      \
     cudaError_t _e = (call);                                                \
     if (_e != cudaSuccess) {                                                \
       ctx->err = std::string(#call) + " -> " + cudaGetErrorString(_e);      \
-      cleanup();                                                            \
       return B200_ERR_CUDA;                                                 \
     }                                                                       \
   } while (0)
@@ -134,7 +138,6 @@ extern "C" int b200_solve_coo_h(b200_ctx* ctx, const int32_t* row_h, const int32
     CKX(cudaMemcpyAsync(x_h, dx, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CKX(cudaStreamSynchronize(ctx->stream));
   }
-  cleanup();
 #undef CKX
   return rc;
 }

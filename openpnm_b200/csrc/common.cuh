@@ -144,6 +144,7 @@ struct b200_ctx {
   // workspaces
   DevBuf w_cnt, w_keys, w_scan, w_part, w_ticket, w_flags, w_tmp0, w_tmp1, w_tmp2;
   int* flags_h = nullptr;      // pinned
+  DevBuf h_row, h_col, h_dat, h_vec;   // device staging of b200_solve_coo_h
 
   // statistics
   b200_stats stats{};

@@ -162,3 +162,31 @@ def test_golden_cubic50_direct_solve(b2, golden, golden_meta):
     for lbl in ("left", "right"):
         r = sf.rate(pores=g["pores_" + lbl])[0]
         assert abs(r - m["rates"][lbl]) <= 1e-8 * abs(m["rates"][lbl])
+
+
+def test_cg_vs_cg_cubic_100(b2):
+    """above 50^3 there is no direct-solve oracle, so the GPU
+    PCG is checked against the oracle's numpy Jacobi-PCG at rtol 1e-13 (1 M pores)."""
+    n = 100
+    pn = b2.Cubic([n, n, n], spacing=1e-4, coords=False)
+    g = hetero(pn.Nt)
+    bcv = np.full(pn.Np, np.nan)
+    bcv[pn.pores("left")] = 2e5
+    bcv[pn.pores("right")] = 1e5
+    A, b, f = oracle.apply_bcs(oracle.build_A(pn.conns, g, pn.Np), pn.Np, bcv, None)
+    M = oracle.to_csr(A, pn.Np)
+    xr, info, its_ref = oracle.jacobi_pcg(M, b, rtol=1e-13)
+    assert info == 0
+    ph = b2.Phase(pn)
+    ph["throat.hydraulic_conductance"] = g
+    sf = b2.StokesFlow(network=pn, phase=ph)
+    sf["pore.bc.value"] = bcv
+    sf.run(solver=b2.B200PCG(tol=1e-13))
+    assert sf.soln.is_converged
+    assert np.max(np.abs(sf.x - xr) / np.abs(xr)) < 1e-8
+    assert abs(sf.soln.cg_iters - its_ref) <= 0.1 * its_ref + 70
+    A_gpu = sf.A
+    assert np.array_equal(A_gpu.indptr, M.indptr) and np.array_equal(A_gpu.indices, M.indices)
+    rl = sf.rate(pores=pn.pores("left"))[0]
+    rref = oracle.rate(pn.conns, g, xr, pores=pn.pores("left"))[0]
+    assert abs(rl - rref) <= 1e-8 * abs(rref)
