@@ -147,3 +147,27 @@ def test_reference_advection_diffusion_with_b200(op, b2):
     x = [0., 0., 0., 0.89653, 0.89653, 0.89653, 1.53924, 1.53924, 1.53924, 2., 2., 2.]
     np.testing.assert_allclose(ad["pore.concentration"], x, rtol=1e-5, atol=1e-12)
     assert ad.soln.is_converged
+
+
+def test_integration_md_stub_runs_verbatim(op, b2):
+    """The ctypes binding printed in INTEGRATION.md section 1, executed as written
+    (only the library path is made absolute) inside the real OpenPNM."""
+    import re
+    import types
+    from openpnm_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(# openpnm/solvers/_b200\.py\n.*?)```", md, re.S).group(1)
+    code = code.replace("'libb200pnm.so'", repr(_lib.LIB_PATH))
+    mod = types.ModuleType("openpnm.solvers._b200")
+    exec(compile(code, "INTEGRATION.md", "exec"), mod.__dict__)
+    op.solvers.B200PCG_stub = mod.B200PCG
+    pn = op.network.Cubic(shape=[9, 9, 9])
+    ph = op.phase.Phase(network=pn)
+    ph["throat.hydraulic_conductance"] = 1.0
+    sf = op.algorithms.StokesFlow(network=pn, phase=ph)
+    sf.set_value_BC(pores=pn.pores("top"), values=101325)
+    sf.set_value_BC(pores=pn.pores("bottom"), values=0)
+    sf.run(solver=mod.B200PCG(tol=1e-12))
+    np.testing.assert_allclose(sf.rate(pores=pn.pores("top"))[0], 1025915.625, rtol=1e-9)
+    assert sf.soln.is_converged
