@@ -175,6 +175,22 @@ int b200_picard(b200_ctx* ctx, const double* x0, double relaxation,
                 int64_t* num_iter, int* converged, int64_t* cg_iters_total,
                 int* last_info);
 
+/* Same loop with the reference's `_update_iterative_props` hook
+ * (_algorithm.py:69-91, called from _update_A_and_b, _reactive_transport.py:
+ * 226-232): `update(user, x_dev)` runs before the first residual and after
+ * every relaxed update, with the stream idle and x (n,) on the device.  It may
+ * regenerate host-side pore-scale models at x and hand the result back with
+ * b200_build_laplacian / b200_apply_bcs (variable conductance) and
+ * b200_clear_sources / b200_add_source (B200_SRC_LINEAR with S1, S2 arrays for
+ * a model that has no device kernel).  Non-zero return aborts the loop with
+ * B200_ERR_ARG.  Single GPU only.                                           */
+typedef int (*b200_update_fn)(void* user, const double* x_dev);
+int b200_picard_cb(b200_ctx* ctx, const double* x0, double relaxation,
+                   int64_t newton_maxiter, double f_rtol, double x_rtol,
+                   double cg_rtol, int64_t cg_maxiter, double* x,
+                   int64_t* num_iter, int* converged, int64_t* cg_iters_total,
+                   int* last_info, b200_update_fn update, void* user);
+
 /* ------------------------------------------------ transient (explicit RK45)
  * Replaces TransientReactiveTransport.run + _build_rhs
  * (openpnm/algorithms/_transient_reactive_transport.py:51-123) with

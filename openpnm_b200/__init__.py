@@ -15,8 +15,10 @@ and the in-tree libb200pnm.so -- there is no CPU fallback.
 """
 from . import _lib, algorithms, integrators, network, solvers
 from .algorithms import (AdvectionDiffusion, FickianDiffusion, FourierConduction, OhmicConduction,
-                         ReactiveTransport, StokesFlow, TransientFickianDiffusion,
-                         TransientReactiveTransport, Transport)
+                         ReactiveTransport, SolutionContainer, SteadyStateSolution, StokesFlow,
+                         TransientAdvectionDiffusion, TransientFickianDiffusion,
+                         TransientFourierConduction, TransientOhmicConduction,
+                         TransientReactiveTransport, TransientSolution, Transport)
 from .integrators import B200RK45
 from .network import Cubic, Network, Phase
 from .solvers import B200PCG

@@ -20,6 +20,9 @@ FMT_NONE, FMT_CSR, FMT_DIA = 0, 1, 2
 FMT_NAMES = {0: "none", 1: "csr", 2: "dia"}
 
 
+UPDATE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)   # b200_update_fn
+
+
 class B200Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libb200pnm error {ERR_NAMES.get(code, code)}: {msg}")
@@ -71,6 +74,8 @@ SIGNATURES = {
     "b200_add_source": (C.c_int, [_p, C.c_int, _p, _p, _p, _p]),
     "b200_picard": (C.c_int, [_p, _p, _dbl, _i64, _dbl, _dbl, _dbl, _i64, _p, _pi64, _pint,
                               _pi64, _pint]),
+    "b200_picard_cb": (C.c_int, [_p, _p, _dbl, _i64, _dbl, _dbl, _dbl, _i64, _p, _pi64, _pint,
+                                 _pi64, _pint, _p, _p]),
     "b200_transient_rk45": (C.c_int, [_p, _p, _p, _dbl, _dbl, _dbl, _dbl, _p, _i64, _i64, _p, _p,
                                       _pi64, _pi64, _pi64, _pint]),
     "b200_rate_pores": (C.c_int, [_p, _p, _p, _i64, _p]),

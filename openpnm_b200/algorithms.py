@@ -143,9 +143,29 @@ class Transport(dict):
                 return {}          # _transport.py:76-83
             raise KeyError(key)
 
+    _missing = object()
+
+    def pop(self, key, default=_missing):
+        """dict.pop that also removes a nested prefix ('pore.source' drops every
+        'pore.source.*'), as the reference's Base2 does (_base2.py:166-177)."""
+        if dict.__contains__(self, key):
+            return dict.pop(self, key)
+        pre = key + "."
+        hits = {k[len(pre):]: dict.pop(self, k) for k in list(self.keys())
+                if k.startswith(pre)}
+        if hits:
+            return hits
+        if default is Transport._missing:
+            raise KeyError(key)
+        return default
+
     @property
     def Ps(self):
         return np.arange(self.Np)
+
+    @property
+    def Ts(self):
+        return np.arange(self.Nt)
 
     @property
     def x(self):
@@ -267,6 +287,9 @@ class Transport(dict):
     def _sources(self):
         return []
 
+    def _n_sources(self):
+        return 0
+
     def _conductance(self):
         g = np.asarray(self._phase[self.settings["conductance"]], dtype=np.float64)
         if g.shape != (self.Nt,):
@@ -280,16 +303,19 @@ class Transport(dict):
         if not (self.settings["cache"] and self._cache_key == key):
             ctx.build_laplacian(self._device_conns(ctx), g, self.Np)
             self._cache_key = key
-        nsrc = len(self._sources())
         f, nnz = ctx.apply_bcs(self["pore.bc.value"], self["pore.bc.rate"],
-                               keep_zero_diag=nsrc > 0)
+                               keep_zero_diag=self._n_sources() > 0)
         return f, nnz
 
     def run(self, solver=None, x0=None, verbose=False):
         """Builds A and b on the GPU, solves, stores the result in `alg.x` and
         `alg.soln` (reference: Transport.run, _transport.py:171-207)."""
         if solver is None:
-            solver = B200PCG()
+            # one default solver per algorithm, so that the Laplacian cached on its
+            # device context survives between runs (settings.cache, _transport.py:108-114)
+            solver = getattr(self, "_default_solver", None)
+            if solver is None:
+                solver = self._default_solver = B200PCG()
         if not getattr(solver, "_b200_native", False):
             raise TypeError("openpnm_b200 algorithms need a B200PCG solver "
                             "(there is no CPU path)")
@@ -320,7 +346,8 @@ class Transport(dict):
                 relaxation=s.get("relaxation_factor", 1.0),
                 newton_maxiter=s.get("newton_maxiter", 5000),
                 f_rtol=s.get("f_rtol", 1e-6), x_rtol=s.get("x_rtol", 1e-6),
-                cg_rtol=cg_rtol, cg_maxiter=0 if solver.maxiter is None else solver.maxiter)
+                cg_rtol=cg_rtol, cg_maxiter=0 if solver.maxiter is None else solver.maxiter,
+                update=self._update_hook(ctx))
         except _lib.B200Error as e:
             if e.code == -4:
                 raise Exception("A or b contains inf/nan values") from e
@@ -342,6 +369,11 @@ class Transport(dict):
 
     def _post_run(self, x):
         pass
+
+    def _update_hook(self, ctx):
+        """Callback for b200_picard_cb, or None when everything that depends on
+        the quantity has a device kernel."""
+        return None
 
     @staticmethod
     def _world_size():
@@ -384,6 +416,7 @@ class Transport(dict):
         if self.settings["validate_topology"]:
             self._validate_topology_health(ctx)
         mask = bdist.slab_throat_mask(conns, rb, re)
+        self._update_hook(None)        # raises if a model needs the host (single-GPU only)
         try:
             srcs = self._sources()
             f, nnz0, nnz = ss.assemble(conns[mask], g[mask], self["pore.bc.value"],
@@ -506,6 +539,116 @@ class ReactiveTransport(Transport):
                          x_rtol=1e-6).items():
             self.settings.setdefault(k, v)
 
+    def _dependency_edges(self):
+        """(upstream, downstream) property pairs of the phase's models: OpenPNM's
+        own graph when the phase is a real one (core/_models.py dependency_graph),
+        else the string arguments of the stand-in Phase's models."""
+        models = getattr(self._phase, "models", None)
+        if models is None:
+            return []
+        if hasattr(models, "dependency_graph"):
+            return [(str(a), str(b)) for a, b in models.dependency_graph(deep=True).edges]
+        edges = []
+        for prop, m in models.items():
+            for k, v in m.items():
+                if k != "model" and isinstance(v, str) and \
+                        v.split(".", 1)[0] in ("pore", "throat"):
+                    edges.append((v, prop.split("@")[0]))
+        return edges
+
+    @property
+    def iterative_props(self):
+        """Properties downstream of the quantity (and of settings.variable_props)
+        in the model dependency graph, in lexicographic topological order; they
+        are regenerated every outer iteration (reference: _algorithm.py:38-67)."""
+        import heapq
+        q = self.settings["quantity"]
+        base = set(self.settings.get("variable_props", ())) | {q}
+        down = {}
+        for a, b in self._dependency_edges():
+            down.setdefault(a, set()).add(b)
+        nodes, stack = set(), [n for n in base if n in down]
+        edges = set()
+        while stack:
+            a = stack.pop()
+            if a in nodes:
+                continue
+            nodes.add(a)
+            for b in down.get(a, ()):
+                edges.add((a, b))
+                stack.append(b)
+        indeg = {n: 0 for n in nodes}
+        for a, b in edges:
+            indeg[b] += 1
+        heap = [n for n, d in indeg.items() if d == 0]
+        heapq.heapify(heap)
+        order = []
+        while heap:
+            a = heapq.heappop(heap)
+            order.append(a)
+            for b in sorted(down.get(a, ())):
+                if (a, b) in edges:
+                    indeg[b] -= 1
+                    if indeg[b] == 0:
+                        heapq.heappush(heap, b)
+        return [n for n in order if n != q]
+
+    def _source_on_host(self, item, iterative):
+        """True when source `item` cannot be evaluated by a device kernel: its
+        model is not one of linear / power_law / standard_kinetics, or one of its
+        parameter arrays itself depends on the quantity."""
+        try:
+            _, m = self._model_of(item)
+        except NotImplementedError:
+            return True
+        return any(isinstance(v, str) and v in iterative
+                   for k, v in m.items() if k not in ("model", "X", "regen_mode"))
+
+    def _update_hook(self, ctx):
+        """_update_iterative_props + _update_A_and_b + _apply_sources for models
+        that live in Python (_algorithm.py:69-91, _reactive_transport.py:125-148,
+        226-232): the device loop hands x back, the phase regenerates the
+        iterative properties, and the new conductance / S1 / S2 go to the device.
+        Returns None when nothing needs the host (the usual case)."""
+        iterative = self.iterative_props
+        items = list(self["pore.source"].keys())
+        host_items = [it for it in items if self._source_on_host(it, iterative)]
+        g_variable = self.settings["conductance"] in iterative
+        if not host_items and not g_variable:
+            return None
+        if self._world_size() > 1:
+            raise NotImplementedError("host-evaluated models run on one GPU")
+        phase, q = self._phase, self.settings["quantity"]
+        dev_items = [it for it in items if it not in host_items]
+        device_terms = dict(zip(dev_items, self._sources_for(dev_items)))
+
+        def update(x_dev):
+            x = self._download(ctx, x_dev)
+            dict.__setitem__(self, q, x)
+            phase[q] = x
+            phase.regenerate_models(propnames=iterative)
+            if g_variable:
+                ctx.build_laplacian(self._device_conns(ctx), self._conductance(), self.Np)
+                self._cache_key = None
+                ctx.apply_bcs(self["pore.bc.value"], self["pore.bc.rate"],
+                              keep_zero_diag=self._n_sources() > 0)
+            ctx.clear_sources()
+            for it in items:
+                mask = np.asarray(self["pore.source." + it], dtype=bool)
+                if it in host_items:
+                    try:
+                        S1 = np.asarray(phase[f"pore.{it}.S1"], dtype=np.float64)
+                        S2 = np.asarray(phase[f"pore.{it}.S2"], dtype=np.float64)
+                    except KeyError:
+                        # the reference stops applying sources at the first model
+                        # that left no S1/S2 (_reactive_transport.py:136-148)
+                        break
+                    ctx.add_source(_lib.SRC_LINEAR, mask, S1, S2, None)
+                else:
+                    _, kind, p1, p2, p3 = device_terms[it]
+                    ctx.add_source(kind, mask, p1, p2, p3)
+        return update
+
     def set_source(self, pores, propname, mode="add"):
         """_reactive_transport.py:70-123"""
         if isinstance(mode, list):
@@ -560,9 +703,19 @@ class ReactiveTransport(Transport):
                 "standard_kinetics are implemented)")
         return name, m
 
+    def _n_sources(self):
+        return len(self["pore.source"])
+
     def _sources(self):
+        """Source terms with a device kernel; the others are handed over by the
+        update hook (`_update_hook`) every outer iteration."""
+        iterative = self.iterative_props
+        return self._sources_for([it for it in self["pore.source"].keys()
+                                  if not self._source_on_host(it, iterative)])
+
+    def _sources_for(self, items):
         out = []
-        for item in self["pore.source"].keys():
+        for item in items:
             mask = np.asarray(self["pore.source." + item], dtype=bool)
             name, m = self._model_of(item)
             if m.get("X", self.settings["quantity"]) != self.settings["quantity"]:
@@ -590,7 +743,10 @@ class ReactiveTransport(Transport):
             self._phase[self.settings["quantity"]] = x
         except Exception:
             return
+        iterative = self.iterative_props
         for item in self["pore.source"].keys():
+            if self._source_on_host(item, iterative):
+                continue            # regenerated on the phase by the update hook
             name, m = self._model_of(item)
             _, keys, defaults = _SRC_KINDS[name]
             p = []
@@ -719,6 +875,10 @@ class TransientReactiveTransport(ReactiveTransport):
         dict.__setitem__(self, q, x0)
         V = np.asarray(self.network[self.settings["pore_volume"]], dtype=np.float64)
         V = V * np.ones(self.Np)
+        if self._update_hook(None) is not None:
+            raise NotImplementedError("transient runs need device-evaluated models "
+                                      "(linear, power_law, standard_kinetics sources; "
+                                      "constant conductance)")
         try:
             self._assemble(ctx)
             ctx.clear_sources()

@@ -60,14 +60,46 @@ __global__ void k_check_finite(const double* __restrict__ a, int64_t n, int* __r
   if (bad) flags[FLAG_NONFINITE] = 1;
 }
 
+// _update_iterative_props + _update_A_and_b through the caller's hook: the hook
+// may re-assemble the system (b200_build_laplacian, b200_apply_bcs) and replace
+// the sources, so every workspace pointer is fetched again afterwards.
+static int picard_update(b200_ctx* ctx, b200_update_fn update, void* user, const double* x,
+                         int64_t n) {
+  if (update) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (update(user, x) != 0) {
+      if (ctx->err.empty() || ctx->err.find("update hook") == std::string::npos)
+        ctx->err = "picard: update hook failed: " + ctx->err;
+      return B200_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_sys || ctx->n != n)
+      FAIL(B200_ERR_ARG, "picard: update hook left no system of the same size");
+    CK(ctx->w_tmp0.ensure((size_t)n * sizeof(double)));
+    CK(ctx->w_part.ensure((size_t)4 * 148 * 16 * sizeof(double)));
+  }
+  return b200_linearize(ctx, x);
+}
+
 extern "C" int b200_picard(b200_ctx* ctx, const double* x0, double relaxation,
                            int64_t newton_maxiter, double f_rtol, double x_rtol, double cg_rtol,
                            int64_t cg_maxiter, double* x, int64_t* num_iter, int* converged,
                            int64_t* cg_iters_total, int* last_info) {
+  return b200_picard_cb(ctx, x0, relaxation, newton_maxiter, f_rtol, x_rtol, cg_rtol, cg_maxiter,
+                        x, num_iter, converged, cg_iters_total, last_info, nullptr, nullptr);
+}
+
+extern "C" int b200_picard_cb(b200_ctx* ctx, const double* x0, double relaxation,
+                              int64_t newton_maxiter, double f_rtol, double x_rtol,
+                              double cg_rtol, int64_t cg_maxiter, double* x, int64_t* num_iter,
+                              int* converged, int64_t* cg_iters_total, int* last_info,
+                              b200_update_fn update, void* user) {
   if (!ctx || !ctx->have_sys || !x) {
     if (ctx) ctx->err = "picard: apply_bcs / load a system first";
     return B200_ERR_ARG;
   }
+  if (update && ctx->nranks > 1)
+    FAIL(B200_ERR_ARG, "picard: the update hook is single-GPU (no slab mode)");
   CK(cudaSetDevice(ctx->device));
   const int64_t n = ctx->n;
   CK(ctx->w_part.ensure((size_t)4 * 148 * 16 * sizeof(double)));
@@ -79,7 +111,6 @@ extern "C" int b200_picard(b200_ctx* ctx, const double* x0, double relaxation,
   CK(ctx->w_tmp0.ensure((size_t)n * sizeof(double)));   // x_new
   RET(b200_zero_flags(ctx));
   int* flags = ctx->w_flags.as<int>();
-  double* xnew = ctx->w_tmp0.as<double>();
   if (x0) {
     if (x0 != x)
       CK(cudaMemcpyAsync(x, x0, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -104,7 +135,7 @@ extern "C" int b200_picard(b200_ctx* ctx, const double* x0, double relaxation,
   } else {
     CK(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), ctx->stream));
   }
-  RET(b200_linearize(ctx, x));
+  RET(picard_update(ctx, update, user, x, n));
 
   double f0 = -1.0, dx2 = 0.0;
   int64_t iters = 0, cg_total = 0;
@@ -129,6 +160,7 @@ extern "C" int b200_picard(b200_ctx* ctx, const double* x0, double relaxation,
       FAIL(B200_ERR_NONFINITE, "A or b contains inf/nan values");
     int64_t its = 0;
     double rel = 0.0;
+    double* xnew = ctx->w_tmp0.as<double>();
     RET(b200_pcg(ctx, x, cg_rtol, 0.0, cg_maxiter, xnew, &its, &rel, &info));
     cg_total += its;
     double* sc = ctx->scal.as<double>();
@@ -140,7 +172,8 @@ extern "C" int b200_picard(b200_ctx* ctx, const double* x0, double relaxation,
     CK(cudaStreamSynchronize(ctx->stream));
     dx2 = first ? 0.0 : ctx->scal_h[SC_AUX0];   // aliasing quirk: first dx == 0
     first = false;
-    RET(b200_linearize(ctx, x));
+    RET(picard_update(ctx, update, user, x, n));
+    flags = ctx->w_flags.as<int>();
     iters = i + 1;
   }
   CK(cudaStreamSynchronize(ctx->stream));

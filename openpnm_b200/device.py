@@ -61,12 +61,18 @@ class Context:
         torch = _torch()
         if isinstance(a, torch.Tensor):
             t = a
-            if dtype is not None and t.dtype != dtype:
-                t = t.to(dtype)
-            if t.device != self.tdev:
-                with torch.cuda.stream(self.stream):
+            if t.is_cuda:
+                # produced on the caller's stream: order this context's stream after it
+                cur = torch.cuda.current_stream(t.device)
+                if cur != self.stream:
+                    self.stream.wait_stream(cur)
+                    t.record_stream(self.stream)
+            with torch.cuda.stream(self.stream):
+                if dtype is not None and t.dtype != dtype:
+                    t = t.to(dtype)
+                if t.device != self.tdev:
                     t = t.to(self.tdev, non_blocking=True)
-            return t.contiguous()
+                return t.contiguous()
         arr = np.ascontiguousarray(a)
         t = torch.from_numpy(arr)
         if dtype is not None and t.dtype != dtype:
@@ -81,6 +87,18 @@ class Context:
 
     def synchronize(self):
         self._ck(self.lib.b200_synchronize(self._h))
+
+    def _publish(self, *ts):
+        """Results are written on this context's stream; make the caller's current
+        torch stream wait for them so plain torch code can use them right away."""
+        torch = _torch()
+        cur = torch.cuda.current_stream(self.tdev)
+        if cur != self.stream:
+            cur.wait_stream(self.stream)
+            for t in ts:
+                if t is not None:
+                    t.record_stream(cur)
+        return ts[0] if len(ts) == 1 else ts
 
     @staticmethod
     def _p(t):
@@ -182,7 +200,7 @@ class Context:
         torch = _torch()
         out = self.empty(self.n, torch.float64)
         self._ck(self.lib.b200_get_b(self._h, self._p(out)))
-        return out
+        return self._publish(out)
 
     def csr_shape(self, which):
         n, nnz = C.c_int64(), C.c_int64()
@@ -197,6 +215,7 @@ class Context:
         ix = self.empty(max(nnz, 1), torch.int32)
         dt = self.empty(max(nnz, 1), torch.float64)
         self._ck(self.lib.b200_export_csr(self._h, which, self._p(ip), self._p(ix), self._p(dt)))
+        self._publish(ip, ix, dt)
         return ip, ix[:nnz], dt[:nnz]
 
     def export_csr_scipy(self, which=_lib.MAT_SYSTEM, ncols=None):
@@ -212,7 +231,7 @@ class Context:
         x = self.to_device(x, torch.float64)
         y = self.empty(self.n, torch.float64)
         self._ck(self.lib.b200_spmv(self._h, which, self._p(x), self._p(y)))
-        return y
+        return self._publish(y)
 
     def set_format(self, fmt=0):
         self._ck(self.lib.b200_set_format(self._h, int(fmt)))
@@ -232,7 +251,7 @@ class Context:
         it, rel, info = C.c_int64(), C.c_double(), C.c_int()
         self._ck(self.lib.b200_pcg(self._h, self._p(x0), float(rtol), float(atol), int(maxiter),
                                    self._p(x), C.byref(it), C.byref(rel), C.byref(info)))
-        return x, it.value, rel.value, info.value
+        return self._publish(x), it.value, rel.value, info.value
 
     def clear_sources(self):
         self._ck(self.lib.b200_clear_sources(self._h))
@@ -257,16 +276,39 @@ class Context:
         self._keep.setdefault("src", []).append((m, t1, t2, t3))
 
     def picard(self, x0=None, relaxation=1.0, newton_maxiter=5000, f_rtol=1e-6, x_rtol=1e-6,
-               cg_rtol=1e-10, cg_maxiter=0):
+               cg_rtol=1e-10, cg_maxiter=0, update=None):
+        """b200_picard; with `update(x_dev_tensor)` the loop calls back before every
+        linearisation (b200_picard_cb) so host-side models can be regenerated."""
         torch = _torch()
         x0 = self.to_device(x0, torch.float64) if x0 is not None else None
         x = self.empty(self.n, torch.float64)
         ni, conv, cgt, info = C.c_int64(), C.c_int(), C.c_int64(), C.c_int()
-        self._ck(self.lib.b200_picard(self._h, self._p(x0), float(relaxation),
-                                      int(newton_maxiter), float(f_rtol), float(x_rtol),
-                                      float(cg_rtol), int(cg_maxiter), self._p(x), C.byref(ni),
-                                      C.byref(conv), C.byref(cgt), C.byref(info)))
-        return x, ni.value, bool(conv.value), cgt.value, info.value
+        if update is None:
+            self._ck(self.lib.b200_picard(self._h, self._p(x0), float(relaxation),
+                                          int(newton_maxiter), float(f_rtol), float(x_rtol),
+                                          float(cg_rtol), int(cg_maxiter), self._p(x),
+                                          C.byref(ni), C.byref(conv), C.byref(cgt),
+                                          C.byref(info)))
+            return self._publish(x), ni.value, bool(conv.value), cgt.value, info.value
+        raised = []
+
+        def hook(_user, _xptr):
+            try:
+                update(x)           # the library iterates in place on this tensor
+                return 0
+            except BaseException as e:      # noqa: BLE001 - re-raised below
+                raised.append(e)
+                return 1
+        cb = _lib.UPDATE_FN(hook)
+        rc = self.lib.b200_picard_cb(self._h, self._p(x0), float(relaxation),
+                                     int(newton_maxiter), float(f_rtol), float(x_rtol),
+                                     float(cg_rtol), int(cg_maxiter), self._p(x), C.byref(ni),
+                                     C.byref(conv), C.byref(cgt), C.byref(info),
+                                     C.cast(cb, C.c_void_p), None)
+        if raised:
+            raise raised[0]
+        self._ck(rc)
+        return self._publish(x), ni.value, bool(conv.value), cgt.value, info.value
 
     def transient_rk45(self, x0, volume, t0, t1, rtol=1e-6, atol=1e-6, saveat=None,
                        capacity=None):
@@ -290,6 +332,7 @@ class Context:
             self._p(out), _lib.np_ptr(times), C.byref(nout), C.byref(nsteps), C.byref(nfev),
             C.byref(status)))
         k = nout.value
+        self._publish(out)
         return times[:k].copy(), out[:k], nsteps.value, nfev.value, status.value
 
     def rate_pores(self, x, pores):
@@ -299,7 +342,7 @@ class Context:
         out = self.empty(pores.numel(), torch.float64)
         self._ck(self.lib.b200_rate_pores(self._h, self._p(x), self._p(pores),
                                           int(pores.numel()), self._p(out)))
-        return out
+        return self._publish(out)
 
     def rate_throats(self, x, throats):
         torch = _torch()
@@ -309,7 +352,7 @@ class Context:
         self._ck(self.lib.b200_rate_throats(self._h, self._p(self._keep["conns"]),
                                             self._p(self._keep["g"]), self._p(x),
                                             self._p(throats), int(throats.numel()), self._p(out)))
-        return out
+        return self._publish(out)
 
     def time_kernel(self, which, reps=20):
         ms = C.c_double()

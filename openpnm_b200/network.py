@@ -110,6 +110,12 @@ class Network(_Store):
                                dtype=bool)
         return np.flatnonzero(mask)
 
+    def num_pores(self, labels="all"):
+        return int(self.pores(labels).size)
+
+    def num_throats(self, labels="all"):
+        return int(self.throats(labels).size)
+
     @property
     def conns(self):
         return dict.__getitem__(self, "throat.conns")
@@ -194,6 +200,23 @@ class Phase(_Store):
         by this package (on the device); `model` is the function or its name."""
         kwargs.pop("regen_mode", None)
         self.models[propname] = dict(model=model, **kwargs)
+
+    def regenerate_models(self, propnames=None):
+        """Run the callable models among `propnames` (all when None) in the given
+        order; a dict result is stored as 'prop.key' entries, the way
+        `ModelsMixin2.run_model` does (openpnm/core/_models.py:483-560).  Models
+        named by a string are device kernels and are skipped here."""
+        for prop in (list(self.models) if propnames is None else propnames):
+            m = self.models.get(prop)
+            if m is None or not callable(m["model"]):
+                continue
+            kwargs = {k: v for k, v in m.items() if k != "model"}
+            vals = m["model"](self, **kwargs)
+            if isinstance(vals, dict):
+                for k, v in vals.items():
+                    self[f"{prop}.{k}"] = v
+            else:
+                self[prop] = vals
 
     def _count(self, key):
         if key.startswith("pore."):

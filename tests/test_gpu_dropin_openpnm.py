@@ -125,6 +125,56 @@ def test_b200_algorithms_accept_reference_objects(op, b2):
     np.testing.assert_allclose(A.data, A_ref.data, rtol=1e-7, atol=0)
 
 
+def test_host_evaluated_models_on_reference_objects(op, b2):
+    """A source model without a device kernel (exponential,
+    source_terms/_funcs.py:172-223) and a conductance that depends on the
+    concentration, both defined on a REAL OpenPNM phase: openpnm_b200 regenerates
+    them through the b200_picard_cb hook exactly where the reference calls
+    _update_iterative_props, so the two outer loops walk the same iterates."""
+    from openpnm.models.physics import source_terms
+    pn = op.network.Cubic(shape=[8, 8, 8], spacing=1e-4)
+    ph = op.phase.Phase(network=pn)
+
+    def D_var(phase, c="pore.concentration"):
+        return 1e-9 * (1 + 0.5 * phase[c] ** 2)
+
+    def g_var(phase, D="pore.diffusivity"):
+        return 1e-6 * phase[D][phase.network.conns].mean(axis=1)
+
+    ph["pore.concentration"] = 0.0
+    ph.add_model(propname="pore.diffusivity", model=D_var)
+    ph.add_model(propname="throat.diffusive_conductance", model=g_var)
+    for k, v in dict(A1=-2e-16, A2=np.e, A3=1.5, A4=1.0, A5=0.0, A6=0.0).items():
+        ph["pore." + k] = v            # r = A1 * A2**(A3 * x**A4 + A5) + A6
+    ph.add_model(propname="pore.rxn", model=source_terms.exponential, X="pore.concentration",
+                 regen_mode="deferred", **{k: "pore." + k for k in
+                                           ("A1", "A2", "A3", "A4", "A5", "A6")})
+    src = pn.pores("right")
+
+    def setup(cls):
+        ph["pore.concentration"] = 0.0
+        ph.regenerate_models()
+        alg = cls(network=pn, phase=ph)
+        alg.settings._update({"conductance": "throat.diffusive_conductance",
+                              "quantity": "pore.concentration"})
+        alg.set_source(pores=src, propname="pore.rxn")
+        alg.set_value_BC(pores=pn.pores("left"), values=1.0)
+        return alg
+
+    ref = setup(op.algorithms.ReactiveTransport)
+    ref.run(solver=op.solvers.ScipySpsolve())
+    c_ref, it_ref = np.array(ref["pore.concentration"]), ref.soln.num_iter
+    q_ref = ref.rate(pores=pn.pores("left"))[0]
+    assert ref.soln.is_converged and it_ref > 3
+
+    alg = setup(b2.ReactiveTransport)
+    assert set(alg.iterative_props) == set(ref.iterative_props)
+    alg.run(solver=b2.B200PCG(tol=1e-13))
+    assert alg.soln.is_converged and alg.soln.num_iter == it_ref
+    assert np.max(np.abs(alg.x - c_ref)) <= 1e-8 * np.max(np.abs(c_ref))
+    assert abs(alg.rate(pores=pn.pores("left"))[0] - q_ref) <= 1e-8 * abs(q_ref)
+
+
 def test_reference_advection_diffusion_with_b200(op, b2):
     """The reference's own AdvectionDiffusion (AdvectionDiffusionTest.py:10-93) solved
     with the B200 solver object: non-symmetric A -> BiCGStab behind the same API."""
