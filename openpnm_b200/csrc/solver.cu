@@ -19,6 +19,7 @@
 // reads i +/- k never need a bounds check; in slab mode the pads are the
 // halo windows filled by the neighbour ranks.
 #include "common.cuh"
+#include <algorithm>
 
 #define PCG_T 256
 
@@ -400,9 +401,13 @@ static int prepare_operator(b200_ctx* ctx) {
   OffTable tab;
   CK(cudaMemcpyAsync(&tab, dtab, sizeof tab, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  // the slots were claimed in race order: sort them, so that the diagonals are
+  // always summed in the same order and repeated solves agree bit for bit
   tab.n = 0;
   for (int k = 0; k < B200_MAX_DIAGS; ++k)
-    if (tab.off[k] != 0) tab.n = k + 1;
+    if (tab.off[k] != 0) tab.off[tab.n++] = tab.off[k];
+  std::sort(tab.off, tab.off + tab.n);
+  for (int k = tab.n; k < B200_MAX_DIAGS; ++k) tab.off[k] = 0;
   const int64_t upper = (ctx->sys_nnz - n) / 2;   // off-diagonals are symmetric pairs
   bool want_dia = !tab.overflow && tab.n > 0 &&
                   (double)upper >= 0.25 * (double)tab.n * (double)n;

@@ -90,6 +90,30 @@ def test_assembly_is_bitwise_repeatable(b2, golden):
             assert np.array_equal(a, b)          # no float atomics anywhere: bit-identical
 
 
+@pytest.mark.parametrize("fmt", ["dia", "csr"])
+def test_solve_is_bitwise_repeatable_on_lattice(fmt, b2):
+    """Same lattice problem on fresh contexts and twice on one context: the DIA
+    operator sums its diagonals in sorted order whatever order the detection
+    kernel's threads found them in, so x and the iteration count repeat exactly."""
+    pn = b2.Cubic([24, 17, 31], coords=False)
+    g = 10.0 ** np.random.default_rng(5).uniform(-15, -12, pn.Nt)
+    bcv = np.full(pn.Np, np.nan)
+    bcv[pn.pores("left")] = 2.0
+    bcv[pn.pores("right")] = 1.0
+    outs = []
+    for rep in range(3):
+        ctx = b2.B200PCG(fmt=fmt).ctx
+        ctx.set_format({"dia": 2, "csr": 1}[fmt])
+        for again in range(2):
+            ctx.build_laplacian(pn.conns, g, pn.Np)
+            ctx.apply_bcs(bcv, None)
+            x, it, rel, info = ctx.pcg(rtol=1e-12)
+            assert info == 0
+            outs.append((x.cpu().numpy().view(np.uint64), it))
+    for o in outs[1:]:
+        assert o[1] == outs[0][1] and np.array_equal(o[0], outs[0][0])
+
+
 def test_b200pcg_solve_dropin_on_reference_style_coo(b2, golden, golden_meta):
     """solver.solve(A=coo, b=b, x0=x0) exactly as _transport.py:213 calls it,
     with A in the reference's own (unsorted, diagonal-last) COO layout."""
