@@ -158,6 +158,26 @@ int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol,
              int* info);
 int b200_pcg_format(b200_ctx* ctx, int* fmt, int* ndiags);
 
+/* ------------------------------- preconditioner behind the same solve call
+ * SURVEY section 8 f-1; the reference's analogue is PyamgRugeStubenSolver
+ * (openpnm/solvers/_pyamg.py:10-17).  B200_PRECOND_AMG makes b200_pcg (and the
+ * solves inside b200_picard) run flexible CG preconditioned by an aggregation
+ * multigrid K-cycle built on the device from the system matrix (csrc/amg.cu):
+ * ~30 iterations at any size instead of O(N) for an N^3 lattice.  Same
+ * stopping rule, same outputs (`iters` counts outer FCG iterations).  Applies
+ * to symmetric single-GPU systems with more than 2048 rows; otherwise, and for
+ * matrices that cannot be coarsened, the call silently stays with Jacobi.
+ * b200_amg_setup builds the hierarchy now (it is otherwise built by the first
+ * solve after the matrix changed); the two accessors export a level's CSR
+ * (level 0 = the system matrix) and its aggregation map (row -> coarse row, -1
+ * for rows left off the coarse grid) for the Galerkin-identity tests.        */
+enum { B200_PRECOND_JACOBI = 0, B200_PRECOND_AMG = 1 };
+int b200_set_precond(b200_ctx* ctx, int kind);
+int b200_amg_setup(b200_ctx* ctx, int* nlevels);
+int b200_amg_level_shape(b200_ctx* ctx, int level, int64_t* n, int64_t* nnz);
+int b200_amg_export_level(b200_ctx* ctx, int level, int32_t* indptr,
+                          int32_t* indices, double* data, int32_t* agg);
+
 /* ------------------------------------------- K5: sources + Picard loop
  * Replaces ReactiveTransport.set_source bookkeeping hand-off,
  * _update_iterative_props (_algorithm.py:69-91), _apply_sources

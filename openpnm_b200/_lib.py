@@ -18,6 +18,8 @@ MAT_PURE, MAT_SYSTEM = 0, 1
 SRC_LINEAR, SRC_POWER_LAW, SRC_STANDARD_KINETICS = 0, 1, 2
 FMT_NONE, FMT_CSR, FMT_DIA = 0, 1, 2
 FMT_NAMES = {0: "none", 1: "csr", 2: "dia"}
+PRECOND_JACOBI, PRECOND_AMG = 0, 1
+PRECOND_CODES = {"jacobi": 0, "amg": 1}
 
 
 UPDATE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)   # b200_update_fn
@@ -70,6 +72,10 @@ SIGNATURES = {
     "b200_pcg_prepare": (C.c_int, [_p, C.c_int]),
     "b200_pcg": (C.c_int, [_p, _p, _dbl, _dbl, _i64, _p, _pi64, _pdbl, _pint]),
     "b200_pcg_format": (C.c_int, [_p, _pint, _pint]),
+    "b200_set_precond": (C.c_int, [_p, C.c_int]),
+    "b200_amg_setup": (C.c_int, [_p, _pint]),
+    "b200_amg_level_shape": (C.c_int, [_p, C.c_int, _pi64, _pi64]),
+    "b200_amg_export_level": (C.c_int, [_p, C.c_int, _p, _p, _p, _p]),
     "b200_clear_sources": (C.c_int, [_p]),
     "b200_add_source": (C.c_int, [_p, C.c_int, _p, _p, _p, _p]),
     "b200_picard": (C.c_int, [_p, _p, _dbl, _i64, _dbl, _dbl, _dbl, _i64, _p, _pi64, _pint,

@@ -10,7 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200pnm.so")
-SOURCES = ["api.cu", "assembly.cu", "solver.cu", "picard.cu", "dist.cu", "p2p.cu", "topology.cu", "transient.cu", "bicgstab.cu"]
+SOURCES = ["api.cu", "assembly.cu", "solver.cu", "picard.cu", "dist.cu", "p2p.cu", "topology.cu", "transient.cu", "bicgstab.cu",
+           "amg.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -40,6 +40,7 @@ extern "C" int b200_destroy(b200_ctx* ctx) {
   if (!ctx) return B200_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  b200_amg_release(ctx);
   b200_p2p_release(ctx);
   b200_comm_release(ctx);
   for (DevBuf* b : {&ctx->pure_indptr, &ctx->pure_indices, &ctx->pure_data, &ctx->pure_diag,

@@ -146,6 +146,10 @@ struct b200_ctx {
   int* flags_h = nullptr;      // pinned
   DevBuf h_row, h_col, h_dat, h_vec;   // device staging of b200_solve_coo_h
 
+  // preconditioner: B200_PRECOND_JACOBI or B200_PRECOND_AMG (amg.cu owns `amg`)
+  int precond = 0;
+  void* amg = nullptr;
+
   // statistics
   b200_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -270,6 +274,11 @@ int b200_launch_final(b200_ctx* ctx, const double* xt, double* x);
 const double* b200_cur_diag(b200_ctx* ctx);
 int b200_bicgstab(b200_ctx* ctx, const double* x0, double rtol, double atol, int64_t maxiter,
                   double* x, int64_t* iters, double* relres, int* info);
+// amg.cu
+void b200_amg_release(b200_ctx* ctx);
+bool b200_amg_applicable(b200_ctx* ctx);
+int b200_amg_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol, int64_t maxiter,
+                 double* x, int64_t* iters, double* relres, int* info, int* used);
 // p2p.cu
 void b200_p2p_release(b200_ctx* ctx);
 bool b200_p2p_usable(b200_ctx* ctx);

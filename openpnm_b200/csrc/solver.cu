@@ -899,6 +899,11 @@ extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double ato
   }
   CK(cudaSetDevice(ctx->device));
   if (ctx->nonsym) return b200_bicgstab(ctx, x0, rtol, atol, maxiter, x, iters, relres, info);
+  if (b200_amg_applicable(ctx)) {
+    int used = 0;
+    RET(b200_amg_pcg(ctx, x0, rtol, atol, maxiter, x, iters, relres, info, &used));
+    if (used) return B200_OK;      // otherwise: no hierarchy for this matrix, Jacobi below
+  }
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   RET(b200_pcg_prepare(ctx, ctx->force_fmt));
   CK(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -239,6 +239,35 @@ class Context:
     def pcg_prepare(self, fmt=0):
         self._ck(self.lib.b200_pcg_prepare(self._h, int(fmt)))
 
+    def set_precond(self, kind="jacobi"):
+        self._ck(self.lib.b200_set_precond(self._h, _lib.PRECOND_CODES[kind]))
+
+    def amg_setup(self):
+        """Build the multigrid hierarchy now; returns [(n, nnz), ...] per level."""
+        nl = C.c_int()
+        self._ck(self.lib.b200_amg_setup(self._h, C.byref(nl)))
+        out = []
+        for l in range(nl.value):
+            n, nnz = C.c_int64(), C.c_int64()
+            self._ck(self.lib.b200_amg_level_shape(self._h, l, C.byref(n), C.byref(nnz)))
+            out.append((n.value, nnz.value))
+        return out
+
+    def amg_export_level(self, level, with_agg=True):
+        """(indptr, indices, data, agg) device tensors of one level (agg None if
+        the level is the last one)."""
+        torch = _torch()
+        n, nnz = C.c_int64(), C.c_int64()
+        self._ck(self.lib.b200_amg_level_shape(self._h, level, C.byref(n), C.byref(nnz)))
+        ip = self.empty(n.value + 1, torch.int32)
+        ix = self.empty(max(nnz.value, 1), torch.int32)
+        dt = self.empty(max(nnz.value, 1), torch.float64)
+        ag = self.empty(n.value, torch.int32) if with_agg else None
+        self._ck(self.lib.b200_amg_export_level(self._h, level, self._p(ip), self._p(ix),
+                                                self._p(dt), self._p(ag)))
+        self._publish(ip, ix, dt, ag)
+        return ip, ix[:nnz.value], dt[:nnz.value], ag
+
     def pcg_format(self):
         f, nd = C.c_int(), C.c_int()
         self._ck(self.lib.b200_pcg_format(self._h, C.byref(f), C.byref(nd)))

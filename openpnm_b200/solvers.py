@@ -66,6 +66,12 @@ class B200PCG(IterativeSolver):
     fmt : {'auto', 'csr', 'dia'}
         Operator storage; 'auto' picks symmetric-diagonal storage when the
         matrix has at most 8 distinct super-diagonals (lattice networks).
+    precond : {'jacobi', 'amg'}
+        'amg' preconditions the CG with an aggregation-multigrid K-cycle built
+        on the device (the role `PyamgRugeStubenSolver` plays in the reference,
+        solvers/_pyamg.py:10-17): tens of iterations at any size instead of
+        O(N) on an N^3 lattice.  Same stopping rule; symmetric systems on one
+        GPU with more than 2048 unknowns, Jacobi otherwise.
 
     Returns from ``solve``: ``(x, exit_code)`` with SciPy's convention --
     0 converged, >0 maxiter reached, <0 breakdown (matrix not SPD).
@@ -73,8 +79,12 @@ class B200PCG(IterativeSolver):
 
     _b200_native = True
 
-    def __init__(self, tol=1e-8, maxiter=None, device=None, fmt="auto", distributed=True):
+    def __init__(self, tol=1e-8, maxiter=None, device=None, fmt="auto", distributed=True,
+                 precond="jacobi"):
         super().__init__(tol=tol, maxiter=maxiter)
+        if precond not in _lib.PRECOND_CODES:
+            raise ValueError("precond must be 'jacobi' or 'amg'")
+        self.precond = precond
         if device is None:          # under torchrun: one process per GPU
             import os
             device = int(os.environ.get("LOCAL_RANK", "0"))
@@ -91,6 +101,7 @@ class B200PCG(IterativeSolver):
         if self._ctx is None:
             from .device import Context
             self._ctx = Context(self.device)
+            self._ctx.set_precond(self.precond)
         return self._ctx
 
     def _fmt_code(self):
