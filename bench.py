@@ -354,6 +354,37 @@ def gpu_arm(args):
         traffic = None
     ms_iter = float(np.mean(t_solve_ms)) / max(cg_iters, 1)
 
+    # ---- the same step with the multigrid preconditioner (1 GPU): assemble, build
+    # the hierarchy, solve to the same rtol -- time-to-solve is the metric here,
+    # an AMG iteration is not comparable to a PCG iteration
+    amg = None
+    if world == 1 and not args.no_amg:
+        ctx.set_precond("amg")
+        try:
+            device_step()                               # warm-up (allocates the hierarchy)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(ctx.stream):
+                a0.record()
+                for _ in range(args.steps):
+                    xa, ita, rela, infoa, _nnz = device_step()
+                    sta = ctx.stats()
+                a1.record()
+            barrier()
+            ms_amg = a0.elapsed_time(a1) / args.steps
+            dx = float((xa - x).abs().max() / x.abs().max())
+            amg = {"time_to_solve_s": ms_amg * 1e-3, "iters": int(ita), "relres": rela,
+                   "info": int(infoa), "hierarchy_setup_ms": sta["t_setup_ms"],
+                   "solve_ms": sta["t_solve_ms"], "levels": ctx.amg_setup(),
+                   "max_rel_diff_vs_jacobi_pcg": dx,
+                   "speedup_vs_jacobi_pcg": ms_step / ms_amg,
+                   "what": "B200PCG(precond='amg'): aggregation-AMG K-cycle + flexible CG "
+                           "(csrc/amg.cu); step = assembly + hierarchy build + solve"}
+            del xa
+        finally:
+            ctx.set_precond("jacobi")
+            ss.assemble(conns_d, g_d, bcv_d, None)
+
     # ---- e2e through the public API with HOST buffers: every step copies its
     # inputs from pinned host memory and reads the solution back
     e2e = None
@@ -462,6 +493,8 @@ def gpu_arm(args):
                               "frac_format_bytes": fmt_iter / (ms_iter * 1e-3) / 1e9 / peak,
                               "ms": ms_iter, "kernel_ms": {"K_A": t_ka, "K_BC": t_kb, "K_BC_with_true_norm": t_kc}},
         }
+        if amg:
+            line["amg"] = amg
         if e2e:
             line["e2e"] = e2e
         if cpu:
@@ -485,6 +518,7 @@ def main():
     ap.add_argument("--fmt", default="auto", choices=["auto", "csr", "dia"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-p2p", action="store_true")
+    ap.add_argument("--no-amg", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

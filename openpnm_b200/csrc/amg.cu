@@ -25,6 +25,7 @@
 // Single GPU, symmetric systems; anything else stays with Jacobi-PCG / BiCGStab.
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -33,7 +34,8 @@
 #define AMG_PASSES 3
 #define AMG_COARSEST 2048
 #define AMG_MAX_LEVELS 12
-#define AMG_KLEVELS 2
+#define AMG_KLEVELS_DEFAULT 2
+#define AMG_KLEVELS_MAX 3
 #define AMG_CHEB_RATIO 8.0
 #define AMG_COARSE_ITERS 30
 
@@ -65,10 +67,22 @@ struct AmgState {
   DevBuf t_match, t_prop, t_ids, t_cptr, t_cmem, t_tc, t_tv, t_aggpass, t_cnt, t_cur;
   CsrOut t_csr[2];
   // level 0 lives in the Jacobi-scaled, padded layout of the PCG operator
-  DevBuf z0, ax0, dir0, winv, fd, fq;
+  DevBuf z0, z1, ax0, dir0, winv, fd, fq;
   DevBuf lmax_dev;
   int64_t vlen = 0;
 };
+
+// tuning knob for experiments (B200_AMG_KLEVELS=0..3): levels whose coarse problem
+// gets two inner FCG iterations instead of one cycle
+static int amg_klevels() {
+  static int k = -1;
+  if (k < 0) {
+    const char* e = getenv("B200_AMG_KLEVELS");
+    k = (e && e[0] >= '0' && e[0] <= '0' + AMG_KLEVELS_MAX) ? e[0] - '0' : AMG_KLEVELS_DEFAULT;
+  }
+  return k;
+}
+#define AMG_KLEVELS amg_klevels()
 
 static AmgState* amg_of(b200_ctx* ctx) {
   if (!ctx->amg) ctx->amg = new AmgState();
@@ -82,7 +96,7 @@ void b200_amg_release(b200_ctx* ctx) {
     for (DevBuf* b : {&L.indptr, &L.indices, &L.data, &L.dinv, &L.agg, &L.cptr, &L.cmem, &L.x,
                       &L.b, &L.ax, &L.dir, &L.kb, &L.kc1, &L.kv1, &L.kv2, &L.ks, &L.cgw})
       b->release();
-  for (DevBuf* b : {&A->z0, &A->ax0, &A->dir0, &A->winv, &A->fd, &A->fq, &A->lmax_dev,
+  for (DevBuf* b : {&A->z0, &A->z1, &A->ax0, &A->dir0, &A->winv, &A->fd, &A->fq, &A->lmax_dev,
                     &A->t_match, &A->t_prop, &A->t_ids, &A->t_cptr, &A->t_cmem, &A->t_tc, &A->t_tv,
                     &A->t_aggpass, &A->t_cnt, &A->t_cur})
     b->release();
@@ -380,7 +394,7 @@ __global__ void __launch_bounds__(AMG_T) k_amg_cheb_next(int64_t n,
   }
 }
 
-// bc[I] = sum over members of w (b - ax); w == nullptr: 1
+// bc[I] = sum over members of w (b - ax); w == nullptr: 1; ax == nullptr: b is the residual
 __global__ void __launch_bounds__(AMG_T) k_amg_restrict(int nc, const int* __restrict__ cptr,
                                                         const int* __restrict__ cmem,
                                                         const double* __restrict__ b,
@@ -392,7 +406,7 @@ __global__ void __launch_bounds__(AMG_T) k_amg_restrict(int nc, const int* __res
     double s = 0.0;
     for (int m = cptr[I]; m < cptr[I + 1]; ++m) {
       const int i = cmem[m];
-      const double r = b[i] - ax[i];
+      const double r = ax ? b[i] - ax[i] : b[i];
       s += w ? w[i] * r : r;
     }
     bc[I] = s;
@@ -772,7 +786,7 @@ static int amg_setup(b200_ctx* ctx) {
     C.av = C.data.as<double>();
     RET(amg_level_bound(ctx, A, C, nullptr));
     for (DevBuf* b : {&C.x, &C.b, &C.ax, &C.dir}) CK(b->ensure((size_t)C.n * sizeof(double)));
-    if ((int)(l + 1) <= AMG_KLEVELS) {
+    if ((int)(l + 1) <= AMG_KLEVELS_MAX) {
       for (DevBuf* b : {&C.kb, &C.kc1, &C.kv1, &C.kv2}) CK(b->ensure((size_t)C.n * sizeof(double)));
       CK(C.ks.ensure(8 * sizeof(double)));
     }
@@ -806,12 +820,35 @@ static int amg_spmv(b200_ctx* ctx, AmgState* A, size_t l, const double* x, doubl
 
 // solves A_l x ~ b (x from zero); level 0: b, x, ax, dir are owned pointers of the
 // padded layout, everything in the Jacobi-scaled space
+static int amg_child(b200_ctx* ctx, AmgState* A, size_t l);
+
+// level 0 on the DIA operator: every product is fused with the update that
+// consumes it (k_dia_smooth); zq_aux/zq_out: optional sum zq_aux . x of the result
+static int amg_cycle_fine_dia(b200_ctx* ctx, AmgState* A, const double* b, double* x,
+                              double* xalt, double* res, double* dir, const double* zq_aux,
+                              double* zq_out) {
+  AmgLevel& L = A->lv[0];
+  AmgLevel& C = A->lv[1];
+  const int64_t n = L.n, nc = C.n;
+  double* scratch = ctx->scal.as<double>() + SC_AUX0;
+  const double* w = A->winv.as<double>();
+  RET(b200_dia_smooth(ctx, 1, b, nullptr, nullptr, dir, x, L.c0, L.c1, L.c2, scratch));
+  RET(b200_dia_smooth(ctx, 4, x, b, w, nullptr, res, 0.0, 0.0, 0.0, scratch));
+  LAUNCH(ctx, k_amg_restrict, grid_for(nc, AMG_T), AMG_T, 0, (int)nc, L.cptr.as<int>(),
+         L.cmem.as<int>(), res, nullptr, nullptr, C.b.as<double>());
+  RET(amg_child(ctx, A, 0));
+  LAUNCH(ctx, k_amg_prolong, grid_for(n, AMG_T), AMG_T, 0, n, L.agg.as<int>(), C.x.as<double>(),
+         w, x);
+  RET(b200_dia_smooth(ctx, 2, x, b, nullptr, dir, xalt, L.c0, L.c1, L.c2, scratch));
+  RET(b200_dia_smooth(ctx, 3, xalt, b, zq_aux, dir, x, L.c0, L.c1, L.c2,
+                      zq_aux ? zq_out : scratch));
+  return B200_OK;
+}
+
 static int amg_cycle(b200_ctx* ctx, AmgState* A, size_t l, const double* b, double* x, double* ax,
                      double* dir) {
   AmgLevel& L = A->lv[l];
   const int64_t n = L.n;
-  double* part = ctx->w_part.as<double>();
-  unsigned* ticket = ctx->w_ticket.as<unsigned>();
   if (l + 1 == A->nlev) {
     double* w = L.cgw.as<double>();
     LAUNCH(ctx, k_amg_coarse_cg, 1, 1024, 0, (int)n, L.ip, L.ix, L.av, L.dinv.as<double>(), b, x,
@@ -832,6 +869,25 @@ static int amg_cycle(b200_ctx* ctx, AmgState* A, size_t l, const double* b, doub
   const int gc = grid_for(nc, AMG_T);
   LAUNCH(ctx, k_amg_restrict, gc, AMG_T, 0, (int)nc, L.cptr.as<int>(), L.cmem.as<int>(), b, ax,
          wgt, C.b.as<double>());
+  RET(amg_child(ctx, A, l));
+  LAUNCH(ctx, k_amg_prolong, g, AMG_T, 0, n, L.agg.as<int>(), C.x.as<double>(), wgt, x);
+  // post-smoothing, Chebyshev(2)
+  RET(amg_spmv(ctx, A, l, x, ax));
+  LAUNCH(ctx, k_amg_cheb_first, g, AMG_T, 0, n, dinv, b, ax, L.c0, dir, x);
+  RET(amg_spmv(ctx, A, l, x, ax));
+  LAUNCH(ctx, k_amg_cheb_next, g, AMG_T, 0, n, dinv, b, ax, L.c1, L.c2, dir, x);
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+// coarse-grid correction below level l: C.b holds the restricted residual, the
+// correction comes back in C.x (K-cycle on the finest coarse levels, V below)
+static int amg_child(b200_ctx* ctx, AmgState* A, size_t l) {
+  AmgLevel& C = A->lv[l + 1];
+  const int64_t nc = C.n;
+  const int gc = grid_for(nc, AMG_T);
+  double* part = ctx->w_part.as<double>();
+  unsigned* ticket = ctx->w_ticket.as<unsigned>();
   const bool kcyc = (int)l < AMG_KLEVELS && l + 2 < A->nlev;
   if (kcyc) {
     double* ks = C.ks.as<double>();
@@ -856,13 +912,6 @@ static int amg_cycle(b200_ctx* ctx, AmgState* A, size_t l, const double* b, doub
     RET(amg_cycle(ctx, A, l + 1, C.b.as<double>(), C.x.as<double>(), C.ax.as<double>(),
                   C.dir.as<double>()));
   }
-  LAUNCH(ctx, k_amg_prolong, g, AMG_T, 0, n, L.agg.as<int>(), C.x.as<double>(), wgt, x);
-  // post-smoothing, Chebyshev(2)
-  RET(amg_spmv(ctx, A, l, x, ax));
-  LAUNCH(ctx, k_amg_cheb_first, g, AMG_T, 0, n, dinv, b, ax, L.c0, dir, x);
-  RET(amg_spmv(ctx, A, l, x, ax));
-  LAUNCH(ctx, k_amg_cheb_next, g, AMG_T, 0, n, dinv, b, ax, L.c1, L.c2, dir, x);
-  CK(cudaGetLastError());
   return B200_OK;
 }
 
@@ -888,7 +937,7 @@ int b200_amg_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol, int6
   const int64_t n = ctx->n, pad = ctx->pad;
   if (maxiter <= 0) maxiter = 10 * ctx->n_global;
   const size_t vlen = (size_t)(n + 2 * pad);
-  for (DevBuf* b : {&A->z0, &A->ax0, &A->dir0, &A->fd, &A->fq}) {
+  for (DevBuf* b : {&A->z0, &A->z1, &A->ax0, &A->dir0, &A->fd, &A->fq}) {
     CK(b->ensure(vlen * sizeof(double)));
     CK(cudaMemsetAsync(b->p, 0, vlen * sizeof(double), ctx->stream));
   }
@@ -903,6 +952,8 @@ int b200_amg_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol, int6
   double* v = ctx->vap.as<double>() + pad;
   double* bt = ctx->vb.as<double>() + pad;
   double* z = A->z0.as<double>() + pad;
+  double* z1 = A->z1.as<double>() + pad;
+  const bool fused = b200_dia_smooth_available(ctx);
   double* ax0 = A->ax0.as<double>() + pad;
   double* dir0 = A->dir0.as<double>() + pad;
   double* d = A->fd.as<double>() + pad;
@@ -943,8 +994,12 @@ int b200_amg_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol, int6
   bool done = !(true2 > tol2);
   bool first = true;
   while (!done && it < maxiter) {
-    RET(amg_cycle(ctx, A, 0, r, z, ax0, dir0));
-    if (!first) LAUNCH(ctx, k_amg_dot1, g, AMG_T, 0, n, z, q, part, ticket, fs + F_ZQ);
+    if (fused) {
+      RET(amg_cycle_fine_dia(ctx, A, r, z, z1, ax0, dir0, first ? nullptr : q, fs + F_ZQ));
+    } else {
+      RET(amg_cycle(ctx, A, 0, r, z, ax0, dir0));
+      if (!first) LAUNCH(ctx, k_amg_dot1, g, AMG_T, 0, n, z, q, part, ticket, fs + F_ZQ);
+    }
     LAUNCH(ctx, k_amg_fcg_dir, g, AMG_T, 0, n, z, r, d, first ? 1 : 0, fs, part, ticket,
            fs + F_DR);
     RET(b200_spmv_dots(ctx, d, r, q, fs + F_DQ));          // fs[F_DQ] = d.q

@@ -272,6 +272,10 @@ int b200_launch_resid(b200_ctx* ctx, const double* bt, const double* ap, const d
                       double* r, double* p, double* out_rr, double* out_true);
 int b200_launch_final(b200_ctx* ctx, const double* xt, double* x);
 const double* b200_cur_diag(b200_ctx* ctx);
+bool b200_dia_smooth_available(b200_ctx* ctx);
+int b200_dia_smooth(b200_ctx* ctx, int mode, const double* p_owned, const double* b_owned,
+                    const double* aux, double* d_owned, double* out_owned, double c0, double c1,
+                    double c2, double* dot_out);
 int b200_bicgstab(b200_ctx* ctx, const double* x0, double rtol, double atol, int64_t maxiter,
                   double* x, int64_t* iters, double* relres, int* info);
 // amg.cu

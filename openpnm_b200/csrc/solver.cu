@@ -582,6 +582,95 @@ __global__ void __launch_bounds__(PCG_T) k_dia_spmv_dot(DiaPack A, const double*
   grid_sum_finalize<3>(v, part, ticket, o, accumulate != 0);
 }
 
+// ---- fine-level multigrid smoothing on the DIA operator (unit diagonal): the
+// product A~ p and the Chebyshev update / weighted residual that consumes it in
+// one pass, written out of place (p is read with its stencil).  amg.cu, level 0.
+//   mode 1  Chebyshev(2) from a zero guess on the right-hand side p:
+//             x1 = c0 p, dd = c1 x1 + c2 (p - c0 y), d = dd, out = x1 + dd
+//   mode 2  first step from x = p:   dd = c0 (b - y),          d = dd, out = p + dd
+//   mode 3  next step from x = p:    dd = c1 d + c2 (b - y),   d = dd, out = p + dd,
+//             and sum aux[i] out[i] (aux may be null)
+//   mode 4  weighted residual:       out = aux[i] (b - y)
+template <int ND>
+__global__ void __launch_bounds__(PCG_T) k_dia_smooth(DiaPack A, int mode,
+                                                      const double* __restrict__ p,
+                                                      const double* __restrict__ b,
+                                                      const double* __restrict__ aux,
+                                                      double* __restrict__ d,
+                                                      double* __restrict__ out, int64_t n,
+                                                      double c0, double c1, double c2, int chunk,
+                                                      double* part, unsigned* ticket,
+                                                      double* dot_out) {
+  const int64_t tile = (int64_t)blockDim.x * chunk;
+  double dot = 0.0;
+  for (int64_t base = (int64_t)blockIdx.x * tile; base < n; base += (int64_t)gridDim.x * tile)
+  for (int c = 0; c < chunk; ++c) {
+    const int64_t i = base + (int64_t)c * blockDim.x + threadIdx.x;
+    if (i >= n) break;
+    const double pi = p[i];
+    double y = pi;
+#pragma unroll
+    for (int m = 0; m < ND; ++m) {
+      const int64_t k = A.off[m];
+      y += A.v[m][i] * p[i + k];
+      y += A.v[m][i - k] * p[i - k];
+    }
+    if (mode == 1) {
+      const double x1 = c0 * pi;
+      const double dd = c1 * x1 + c2 * (pi - c0 * y);
+      d[i] = dd;
+      out[i] = x1 + dd;
+    } else if (mode == 2) {
+      const double dd = c0 * (b[i] - y);
+      d[i] = dd;
+      out[i] = pi + dd;
+    } else if (mode == 3) {
+      const double dd = c1 * d[i] + c2 * (b[i] - y);
+      const double o = pi + dd;
+      d[i] = dd;
+      out[i] = o;
+      if (aux) dot += aux[i] * o;
+    } else {
+      out[i] = aux[i] * (b[i] - y);
+    }
+  }
+  double v[1] = {dot};
+  double* o[1] = {dot_out};
+  grid_sum_finalize<1>(v, part, ticket, o);
+}
+
+bool b200_dia_smooth_available(b200_ctx* ctx) {
+  return ctx->fmt == B200_FMT_DIA && ctx->unit_diag && ctx->nranks == 1;
+}
+
+int b200_dia_smooth(b200_ctx* ctx, int mode, const double* p_owned, const double* b_owned,
+                    const double* aux, double* d_owned, double* out_owned, double c0, double c1,
+                    double c2, double* dot_out) {
+  const int64_t n = ctx->n;
+  double* part = ctx->w_part.as<double>();
+  unsigned* ticket = ctx->w_ticket.as<unsigned>();
+#define SM_CASE(ND)                                                                        \
+  case ND: {                                                                               \
+    static int occ = 0;                                                                    \
+    if (!occ) {                                                                            \
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dia_smooth<ND>, PCG_T, 0)); \
+      if (occ < 1) occ = 1;                                                                \
+    }                                                                                      \
+    int64_t g = (n + PCG_T - 1) / PCG_T;                                                   \
+    if (g > (int64_t)occ * ctx->num_sms) g = (int64_t)occ * ctx->num_sms;                  \
+    if (g < 1) g = 1;                                                                      \
+    LAUNCH(ctx, (k_dia_smooth<ND>), (int)g, PCG_T, 0, ctx->dia, mode, p_owned, b_owned,    \
+           aux, d_owned, out_owned, n, c0, c1, c2, ctx->ka_chunk, part, ticket, dot_out);  \
+  } break;
+  switch (ctx->dia.nd) {
+    SM_CASE(1) SM_CASE(2) SM_CASE(3) SM_CASE(4) SM_CASE(5) SM_CASE(6) SM_CASE(7) SM_CASE(8)
+    default: FAIL(B200_ERR_ARG, "bad diagonal count");
+  }
+#undef SM_CASE
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
 // ---- K_A (CSR-stream): vals/cols streamed coalesced into shared memory as
 // products, then one thread per row adds its segment.
 template <bool UNIT>

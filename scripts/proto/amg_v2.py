@@ -122,7 +122,7 @@ def cycle(levels, l, b, prm):
     VIS[l] = VIS.get(l, 0) + 1
     if l == len(levels) - 1:
         return coarse_cg(L, b, prm['crtol'], prm['cmax'])
-    x = cheb(L, b, None, True, prm['deg'], prm['ratio'])
+    x = cheb(L, b, None, True, prm.get('pre', prm['deg']), prm['ratio'])
     rc = L.P.T @ (b - L.A @ x)
     Lc = levels[l + 1]
     if l < prm['klev'] and l + 1 < len(levels) - 1:
@@ -136,7 +136,7 @@ def cycle(levels, l, b, prm):
     else:
         ec = cycle(levels, l + 1, rc, prm)
     x = x + L.P @ ec
-    return cheb(L, b, x, False, prm['deg'], prm['ratio'])
+    return cheb(L, b, x, False, prm.get('post', prm['deg']), prm['ratio'])
 
 
 def fcg(A, b, M, rtol=1e-10, maxiter=300):
@@ -172,6 +172,7 @@ def main():
     prm = dict(deg=int(sys.argv[3]), ratio=float(sys.argv[4]), klev=int(sys.argv[5]),
                crtol=float(sys.argv[6]), cmax=int(sys.argv[7]))
     passes = int(sys.argv[8]) if len(sys.argv) > 8 else 3
+    if len(sys.argv) > 10: prm['pre'] = int(sys.argv[9]); prm['post'] = int(sys.argv[10])
     A, b = problem(kind, N)
     t0 = time.time(); levels = setup(A, passes=passes)
     print('levels', [L.n for L in levels], 'nnz', [L.A.nnz for L in levels], 'lmax', ['%.2f' % L.lmax for L in levels], 'setup %.1fs' % (time.time() - t0))
