@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <math.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include "common.cuh"
 
@@ -42,6 +43,7 @@
 struct AmgLevel {
   int64_t n = 0, nnz = 0, nc = 0;
   DevBuf indptr, indices, data, dinv;   // own CSR (levels >= 1)
+  DevBuf dataf;                         // fp32 copy of the values for the cycle's products
   const int* ip = nullptr;
   const int* ix = nullptr;
   const double* av = nullptr;
@@ -84,6 +86,16 @@ static int amg_klevels() {
 }
 #define AMG_KLEVELS amg_klevels()
 
+// B200_AMG_F32=0 keeps the coarse operators in fp64 (A/B experiments)
+static bool amg_f32() {
+  static int k = -1;
+  if (k < 0) {
+    const char* e = getenv("B200_AMG_F32");
+    k = (e && e[0] == '0') ? 0 : 1;
+  }
+  return k != 0;
+}
+
 static AmgState* amg_of(b200_ctx* ctx) {
   if (!ctx->amg) ctx->amg = new AmgState();
   return static_cast<AmgState*>(ctx->amg);
@@ -94,7 +106,7 @@ void b200_amg_release(b200_ctx* ctx) {
   AmgState* A = static_cast<AmgState*>(ctx->amg);
   for (AmgLevel& L : A->lv)
     for (DevBuf* b : {&L.indptr, &L.indices, &L.data, &L.dinv, &L.agg, &L.cptr, &L.cmem, &L.x,
-                      &L.b, &L.ax, &L.dir, &L.kb, &L.kc1, &L.kv1, &L.kv2, &L.ks, &L.cgw})
+                      &L.b, &L.ax, &L.dir, &L.kb, &L.kc1, &L.kv1, &L.kv2, &L.ks, &L.cgw, &L.dataf})
       b->release();
   for (DevBuf* b : {&A->z0, &A->z1, &A->ax0, &A->dir0, &A->winv, &A->fd, &A->fq, &A->lmax_dev,
                     &A->t_match, &A->t_prop, &A->t_ids, &A->t_cptr, &A->t_cmem, &A->t_tc, &A->t_tv,
@@ -352,6 +364,36 @@ __global__ void __launch_bounds__(AMG_T) k_amg_rowbound(const int* __restrict__ 
 }
 
 // ============================================================== cycle kernels
+// Coarse-level product y = A x with the values held in fp32 (the coarse operators
+// only precondition: 8 instead of 12 bytes per entry); x, y and the sums stay fp64.
+// 8 lanes per row, warp-uniform trip count (see k_spmv_csr_vec).
+__global__ void __launch_bounds__(256) k_amg_spmv_f32(const int* __restrict__ indptr,
+                                                      const int* __restrict__ indices,
+                                                      const float* __restrict__ data, int64_t n,
+                                                      const double* __restrict__ x,
+                                                      double* __restrict__ y) {
+  const int lane = threadIdx.x % 8;
+  const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) / 8;
+  const int64_t nround = (n + 3) / 4 * 4;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8; r < nround; r += gstride) {
+    double s = 0.0;
+    if (r < n) {
+      const int e1 = indptr[r + 1];
+      for (int e = indptr[r] + lane; e < e1; e += 8) s += (double)data[e] * x[indices[e]];
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, 8);
+    if (lane == 0 && r < n) y[r] = s;
+  }
+}
+
+__global__ void __launch_bounds__(AMG_T) k_amg_to_f32(int64_t n, const double* __restrict__ a,
+                                                      float* __restrict__ o) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    o[i] = (float)a[i];
+}
+
 // dinv == nullptr: unit diagonal (level 0, Jacobi-scaled operator)
 __global__ void __launch_bounds__(AMG_T) k_amg_cheb_first0(int64_t n,
                                                            const double* __restrict__ dinv,
@@ -491,15 +533,27 @@ __global__ void __launch_bounds__(AMG_T) k_amg_kcomb(int64_t n, const double* __
     x[i] = f1 * c1[i] + f2 * x[i];
 }
 
-// Jacobi-CG on the coarsest level inside one thread block (n <= a few thousand)
-__device__ __forceinline__ double block_sum_all(double v) {
-  __shared__ double bc;
-  v = block_sum(v);
-  if (threadIdx.x == 0) bc = v;
+// Jacobi-CG on the coarsest level inside one thread block (n <= a few thousand).
+// Two block reductions per iteration, each one barrier: warp sums go to one of
+// two alternating shared slots and every thread adds the 32 of them itself.
+template <int NV>
+__device__ __forceinline__ void cg_block_sums(double (&v)[NV], double (*slot)[32], int& flip) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double (*sl)[32] = slot + flip * NV;
+  flip ^= 1;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double s = warp_sum(v[k]);
+    if (lane == 0) sl[k][w] = s;
+  }
   __syncthreads();
-  v = bc;
-  __syncthreads();
-  return v;
+  const int nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = 0.0;
+    for (int i = 0; i < nw; ++i) s += sl[k][i];
+    v[k] = s;
+  }
 }
 
 __global__ void __launch_bounds__(1024) k_amg_coarse_cg(int n, const int* __restrict__ ip,
@@ -512,44 +566,48 @@ __global__ void __launch_bounds__(1024) k_amg_coarse_cg(int n, const int* __rest
                                                         double* __restrict__ p,
                                                         double* __restrict__ q, int maxit,
                                                         double rtol2) {
-  double s_rz = 0.0, s_b2 = 0.0;
+  __shared__ double slot[2 * 2][32];
+  int flip = 0;
+  double v2[2] = {0.0, 0.0};
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double bi = b[i], z = dinv[i] * bi;
     x[i] = 0.0;
     r[i] = bi;
     p[i] = z;
-    s_rz += bi * z;
-    s_b2 += bi * bi;
+    v2[0] += bi * z;
+    v2[1] += bi * bi;
   }
-  double rz = block_sum_all(s_rz);
-  const double b2 = block_sum_all(s_b2);
+  cg_block_sums<2>(v2, slot, flip);      // the barrier inside also publishes p
+  double rz = v2[0];
+  const double b2 = v2[1];
   if (!(b2 > 0.0) || !(rz > 0.0)) return;
   for (int it = 0; it < maxit; ++it) {
-    double s_pq = 0.0;
+    double v1[2] = {0.0, 0.0};
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       double s = 0.0;
       for (int e = ip[i]; e < ip[i + 1]; ++e) s += av[e] * p[ix[e]];
       q[i] = s;
-      s_pq += p[i] * s;
+      v1[0] += p[i] * s;
     }
-    const double pq = block_sum_all(s_pq);      // also orders q/p accesses of the next loops
+    cg_block_sums<2>(v1, slot, flip);    // every thread is past its reads of p
+    const double pq = v1[0];
     if (!(pq > 0.0)) return;
     const double al = rz / pq;
-    double s_rr = 0.0, s_rzn = 0.0;
+    double v[2] = {0.0, 0.0};
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       x[i] += al * p[i];
       const double ri = r[i] - al * q[i];
       r[i] = ri;
-      s_rr += ri * ri;
-      s_rzn += ri * ri * dinv[i];
+      v[0] += ri * ri;
+      v[1] += ri * ri * dinv[i];
     }
-    const double rr = block_sum_all(s_rr);
-    const double rzn = block_sum_all(s_rzn);
+    cg_block_sums<2>(v, slot, flip);
+    const double rr = v[0], rzn = v[1];
     if (rr <= rtol2 * b2 || !(rzn > 0.0)) return;
     const double beta = rzn / rz;
     rz = rzn;
     for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = dinv[i] * r[i] + beta * p[i];
-    __syncthreads();
+    __syncthreads();                     // p complete before the next product gathers it
   }
 }
 
@@ -738,6 +796,14 @@ static int amg_setup(b200_ctx* ctx) {
     RET(amg_level_bound(ctx, A, L, diag0));
   }
   size_t l = 0;
+  double t_prev = 0.0;
+  auto now_ms = [&]() {
+    cudaStreamSynchronize(ctx->stream);
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  };
+  if (ctx->debug) t_prev = now_ms();
   while (l + 1 < AMG_MAX_LEVELS && A->lv[l].n > AMG_COARSEST) {
     if (A->lv.size() <= l + 1) A->lv.emplace_back();     // may move the vector: index, never keep refs
     const int n = (int)A->lv[l].n;
@@ -767,6 +833,12 @@ static int amg_setup(b200_ctx* ctx) {
       if (pass > 0)
         LAUNCH(ctx, k_amg_compose, grid_for(n, AMG_T), AMG_T, 0, n, A->lv[l].agg.as<int>(),
                aggp.as<int>());
+      if (ctx->debug) {
+        const double t = now_ms();
+        fprintf(stderr, "[b200 amg] level %d pass %d: %lld -> %lld rows, %lld nnz, %.2f ms\n",
+                (int)l, pass, (long long)nn, (long long)dst.n, (long long)dst.nnz, t - t_prev);
+        t_prev = t;
+      }
       ip = dst.indptr.as<int>();
       ix = dst.indices.as<int>();
       av = dst.data.as<double>();
@@ -785,6 +857,10 @@ static int amg_setup(b200_ctx* ctx) {
     C.ix = C.indices.as<int>();
     C.av = C.data.as<double>();
     RET(amg_level_bound(ctx, A, C, nullptr));
+    if (amg_f32()) {
+      CK(C.dataf.ensure((size_t)(C.nnz > 0 ? C.nnz : 1) * sizeof(float)));
+      LAUNCH(ctx, k_amg_to_f32, grid_for(C.nnz, AMG_T), AMG_T, 0, C.nnz, C.av, C.dataf.as<float>());
+    }
     for (DevBuf* b : {&C.x, &C.b, &C.ax, &C.dir}) CK(b->ensure((size_t)C.n * sizeof(double)));
     if ((int)(l + 1) <= AMG_KLEVELS_MAX) {
       for (DevBuf* b : {&C.kb, &C.kc1, &C.kv1, &C.kv2}) CK(b->ensure((size_t)C.n * sizeof(double)));
@@ -815,6 +891,11 @@ static int amg_setup(b200_ctx* ctx) {
 static int amg_spmv(b200_ctx* ctx, AmgState* A, size_t l, const double* x, double* y) {
   if (l == 0) return b200_spmv_dots(ctx, x, x, y, ctx->scal.as<double>() + SC_AUX0);
   AmgLevel& L = A->lv[l];
+  if (amg_f32()) {
+    LAUNCH(ctx, k_amg_spmv_f32, grid_for(L.n * 8, 256), 256, 0, L.ip, L.ix, L.dataf.as<float>(),
+           L.n, x, y);
+    return B200_OK;
+  }
   return b200_spmv_csr_raw(ctx, L.ip, L.ix, L.av, L.n, 0, x, y);
 }
 
@@ -867,8 +948,8 @@ static int amg_cycle(b200_ctx* ctx, AmgState* A, size_t l, const double* b, doub
   AmgLevel& C = A->lv[l + 1];
   const int64_t nc = C.n;
   const int gc = grid_for(nc, AMG_T);
-  LAUNCH(ctx, k_amg_restrict, gc, AMG_T, 0, (int)nc, L.cptr.as<int>(), L.cmem.as<int>(), b, ax,
-         wgt, C.b.as<double>());
+  LAUNCH(ctx, k_amg_restrict, gc, AMG_T, 0, (int)nc, L.cptr.as<int>(), L.cmem.as<int>(), b,
+         ax, wgt, C.b.as<double>());
   RET(amg_child(ctx, A, l));
   LAUNCH(ctx, k_amg_prolong, g, AMG_T, 0, n, L.agg.as<int>(), C.x.as<double>(), wgt, x);
   // post-smoothing, Chebyshev(2)

@@ -178,3 +178,35 @@ def test_amg_iterations_do_not_grow_and_runs_repeat(b2):
         if len(res) == 2:
             assert res[0][1] == res[1][1] and np.array_equal(res[0][0], res[1][0])
     assert its[32] <= 40 and its[64] <= its[32] + 8
+
+
+def test_amg_with_dead_throats_and_production_source(b2):
+    """Zero conductances (rows that lose neighbours, some pores isolated from the
+    hierarchy) and a source with S1 > 0 (production: the diagonal shrinks)."""
+    pn = b2.Cubic([18, 17, 16], coords=False)
+    rng = np.random.default_rng(11)
+    g = 10.0 ** rng.uniform(-15, -12, pn.Nt)
+    g[rng.random(pn.Nt) < 0.15] = 0.0
+    d = np.zeros(pn.Np)
+    np.add.at(d, pn.conns[:, 0], g)
+    np.add.at(d, pn.conns[:, 1], g)
+    assert (d == 0).sum() >= 1                    # at least one pore lost all its throats
+    A1 = np.where(d > 4e-16, 2e-16, -2e-16)       # production wherever the diagonal stays positive
+    out = {}
+    for precond in ("jacobi", "amg"):
+        ph = _phase(b2, pn, g, "throat.diffusive_conductance")
+        ph["pore.A1"], ph["pore.A2"] = A1, 1e-15
+        ph.add_model(propname="pore.rxn", model="linear", A1="pore.A1", A2="pore.A2",
+                     X="pore.concentration")
+        rt = b2.ReactiveTransport(network=pn, phase=ph)
+        rt.settings._update({"quantity": "pore.concentration",
+                             "conductance": "throat.diffusive_conductance",
+                             "validate_topology": False})
+        rt.set_value_BC(pores=pn.pores("left"), values=1.0)
+        rt.set_value_BC(pores=pn.pores("right"), values=0.0)
+        interior = np.setdiff1d(pn.Ps, np.r_[pn.pores("left"), pn.pores("right")])
+        rt.set_source(pores=interior, propname="pore.rxn")
+        rt.run(solver=b2.B200PCG(tol=1e-12, precond=precond))
+        assert rt.soln.is_converged
+        out[precond] = np.array(rt.x)
+    assert np.max(np.abs(out["amg"] - out["jacobi"])) <= 1e-8 * np.max(np.abs(out["jacobi"]))

@@ -46,6 +46,25 @@ def test_reference_stokesflow_with_b200pcg(op, b2):
     assert solver.info["fmt"] == "dia" and solver.info["exit_code"] == 0
 
 
+def test_reference_stokesflow_with_b200_multigrid(op, b2):
+    """`B200PCG(precond='amg')` in the seat of the reference's PyamgRugeStubenSolver
+    (solvers/_pyamg.py:10-17): the reference assembles, the device builds the
+    hierarchy from the COO it is handed and solves."""
+    pn = op.network.Cubic(shape=[15, 15, 15], spacing=1e-4)
+    ph = op.phase.Phase(network=pn)
+    ph["throat.hydraulic_conductance"] = hetero(pn.Nt, 4)
+    sf = op.algorithms.StokesFlow(network=pn, phase=ph)
+    sf.set_value_BC(pores=pn.pores("left"), values=2e5)
+    sf.set_rate_BC(pores=pn.pores("right"), rates=-1e-9)
+    sf.run(solver=op.solvers.ScipySpsolve())
+    x_ref = np.array(sf.x)
+    solver = b2.B200PCG(tol=1e-13, precond="amg")
+    sf.run(solver=solver)
+    assert sf.soln.is_converged
+    assert np.max(np.abs(sf.x - x_ref)) <= 1e-8 * np.max(np.abs(x_ref))
+    assert solver.info["exit_code"] == 0 and solver.info["iters"] <= 40
+
+
 def test_default_solver_registration(op, b2):
     """op.Workspace().settings.default_solver = 'B200PCG' (utils/_workspace.py:44-56)."""
     b2.register_with_openpnm(op)
