@@ -414,6 +414,21 @@ def gpu_arm(args):
                "d2h_bytes_per_step": int(8 * Np + 8 * left.size),
                "ms_per_step": 1e3 * t_e2e, "api": "openpnm_b200.StokesFlow.run + rate",
                "rate_inlet": float(qq)}
+        if amg is not None:
+            # the same public call with the multigrid preconditioner (host buffers in and out)
+            ctx.set_precond("amg")
+            try:
+                sf.run(solver=solver)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    sf.run(solver=solver)
+                    qa = sf.rate(pores=left)[0]
+                torch.cuda.synchronize()
+                amg["e2e_time_to_solve_s"] = (time.perf_counter() - t0) / args.steps
+                amg["e2e_rate_inlet"] = float(qa)
+            finally:
+                ctx.set_precond("jacobi")
     else:
         # slab API (openpnm_b200.dist.SlabSolver): each rank uploads the throats of its
         # slab + the BC array, assembles, solves and downloads its part of x
