@@ -63,7 +63,7 @@ struct CsrOut {
 struct AmgState {
   std::vector<AmgLevel> lv;      // buffers persist across setups; nlev of them are live
   size_t nlev = 0;
-  uint64_t epoch = ~0ull;
+  uint64_t epoch = ~0ull, lin_epoch = ~0ull;
   bool valid = false;
   // setup temporaries, kept so that a rebuild of the same size allocates nothing
   DevBuf t_match, t_prop, t_ids, t_cptr, t_cmem, t_tc, t_tv, t_aggpass, t_cnt, t_cur;
@@ -877,6 +877,7 @@ static int amg_setup(b200_ctx* ctx) {
     FAIL(B200_ERR_SINGULAR, "amg: a coarse matrix has a non-positive diagonal");
   A->valid = A->nlev > 1;
   A->epoch = ctx->sys_epoch;
+  A->lin_epoch = ctx->lin_epoch;
   if (ctx->debug) {
     fprintf(stderr, "[b200 amg] levels:");
     for (size_t k = 0; k < A->nlev; ++k)
@@ -1011,7 +1012,10 @@ int b200_amg_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol, int6
   RET(b200_pcg_prepare(ctx, ctx->force_fmt));
   if (!ctx->unit_diag) return B200_OK;
   AmgState* A = amg_of(ctx);
-  if (A->epoch != ctx->sys_epoch || A->nlev == 0) RET(amg_setup(ctx));
+  // a re-linearised source term moves the diagonal: coarse operators built from the
+  // old one precondition badly (config 5: 250 instead of 31 iterations), so rebuild
+  if (A->epoch != ctx->sys_epoch || A->lin_epoch != ctx->lin_epoch || A->nlev == 0)
+    RET(amg_setup(ctx));
   if (!A->valid) return B200_OK;
   *used = 1;
   CK(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -122,6 +122,7 @@ struct b200_ctx {
   SrcPack srcs{};
   DevBuf diag_eff, b_eff;     // linearised diagonal and rhs
   bool lin_valid = false;
+  uint64_t lin_epoch = 0;     // bumped by every re-linearisation of the sources
 
   // PCG operator (Jacobi-scaled, unit diagonal)
   uint64_t op_epoch = ~0ull;

@@ -153,6 +153,7 @@ int b200_linearize(b200_ctx* ctx, const double* x) {
          ctx->b_eff.as<double>(), ctx->sys_data.as<double>(), ctx->w_flags.as<int>());
   CK(cudaGetLastError());
   ctx->lin_valid = true;
+  ctx->lin_epoch++;
   ctx->op_epoch = ~0ull;   // scaling depends on the diagonal
   return B200_OK;
 }

@@ -25,7 +25,9 @@ def timed(label, fn):
     return out, time.perf_counter() - t0
 
 
-solver = b2.B200PCG(tol=1e-10)
+PRECOND = sys.argv[1] if len(sys.argv) > 1 else "jacobi"
+print(f"== preconditioner: {PRECOND}", flush=True)
+solver = b2.B200PCG(tol=1e-10, precond=PRECOND)
 
 # config 1: Cubic 50^3 StokesFlow
 pn = b2.Cubic([50, 50, 50], spacing=1e-4, coords=False)
@@ -69,7 +71,7 @@ print(f"config5 Cubic 200^3 ReactiveTransport (power law) run(): {dt:.2f} s, {rt
 
 # config 4: Delaunay, 1M points, trimmed + sorted by x (CSR operator)
 t0 = time.perf_counter()
-npts = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+npts = int(sys.argv[2]) if len(sys.argv) > 2 else 1000000
 pts = np.random.default_rng(0).random((npts, 3))
 c = oracle.delaunay_network(pts)
 L = np.linalg.norm(pts[c[:, 0]] - pts[c[:, 1]], axis=1)
