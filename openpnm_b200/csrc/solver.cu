@@ -18,6 +18,8 @@
 // Vectors live in a padded layout [pad | n owned | pad] so that neighbour
 // reads i +/- k never need a bounds check; in slab mode the pads are the
 // halo windows filled by the neighbour ranks.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include <algorithm>
 
@@ -991,8 +993,26 @@ extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double ato
   if (ctx->nonsym) return b200_bicgstab(ctx, x0, rtol, atol, maxiter, x, iters, relres, info);
   if (b200_amg_applicable(ctx)) {
     int used = 0;
-    RET(b200_amg_pcg(ctx, x0, rtol, atol, maxiter, x, iters, relres, info, &used));
-    if (used) return B200_OK;      // otherwise: no hierarchy for this matrix, Jacobi below
+    int amg_info = 0;
+    // the multigrid-preconditioned solve gets a bounded number of iterations: it
+    // needs ~30 when it works; a matrix it cannot handle (not an M-matrix, say)
+    // is handed to Jacobi-PCG below, starting from the last iterate
+    int64_t amg_cap = 300;
+    if (const char* e = getenv("B200_AMG_MAXITER")) {      // test / tuning knob
+      const long v = strtol(e, nullptr, 10);
+      if (v > 0) amg_cap = v;
+    }
+    if (maxiter > 0 && maxiter < amg_cap) amg_cap = maxiter;
+    RET(b200_amg_pcg(ctx, x0, rtol, atol, amg_cap, x, iters, relres, &amg_info, &used));
+    if (used && amg_info == 0) {
+      if (info) *info = 0;
+      return B200_OK;
+    }
+    if (used) {
+      if (ctx->debug)
+        fprintf(stderr, "[b200 amg] not converged (info %d): continuing with Jacobi-PCG\n", amg_info);
+      if (amg_info > 0) x0 = x;    // finite but slow: keep what was gained; breakdown: start over
+    }
   }
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   RET(b200_pcg_prepare(ctx, ctx->force_fmt));

@@ -211,3 +211,39 @@ def test_amg_with_dead_throats_and_production_source(b2):
         assert rt.soln.is_converged
         out[precond] = np.array(rt.x)
     assert np.max(np.abs(out["amg"] - out["jacobi"])) <= 1e-8 * np.max(np.abs(out["jacobi"]))
+
+
+def test_amg_copes_with_a_non_m_matrix(b2):
+    """Symmetric positive definite, but half of the couplings are positive: the
+    aggregation only sees the negative ones.  The call must still return the solution
+    (by multigrid if it converges, by the Jacobi hand-over otherwise)."""
+    n = 3000
+    rng = np.random.default_rng(5)
+    off = rng.uniform(0.5, 1.0, n - 1) * np.where(rng.random(n - 1) < 0.5, 1.0, -1.0)
+    far = rng.uniform(0.5, 1.0, n - 37) * np.where(rng.random(n - 37) < 0.5, 1.0, -1.0)
+    A = sprs.diags([off, off, far, far], [1, -1, 37, -37], shape=(n, n)).tocsr()
+    A = A + sprs.diags(np.asarray(abs(A).sum(axis=1)).ravel() + 0.01)
+    b = rng.standard_normal(n)
+    x, info = b2.B200PCG(tol=1e-12, precond="amg").solve(A.tocoo(), b)
+    assert info == 0
+    assert np.linalg.norm(A @ x - b) <= 1e-11 * np.linalg.norm(b)
+
+
+def test_amg_hands_over_to_jacobi(b2, monkeypatch):
+    """With the multigrid iteration capped below what it needs (B200_AMG_MAXITER,
+    a test knob read at every call) the same call finishes with Jacobi-PCG from the
+    last iterate: converged, same answer, fewer Jacobi iterations than from zero."""
+    pn, g, bcv = lattice(b2, (20, 18, 16), seed=4)
+    ref = b2.B200PCG(precond="jacobi").ctx
+    ref.build_laplacian(pn.conns, g, pn.Np)
+    ref.apply_bcs(bcv, None)
+    x_ref, it_ref, _, info = ref.pcg(rtol=1e-12)
+    assert info == 0
+    monkeypatch.setenv("B200_AMG_MAXITER", "6")
+    ctx = b2.B200PCG(precond="amg").ctx
+    ctx.build_laplacian(pn.conns, g, pn.Np)
+    ctx.apply_bcs(bcv, None)
+    x, it, rel, info = ctx.pcg(rtol=1e-12)
+    assert info == 0 and rel <= 1e-12 * (1 + 1e-6)
+    assert 40 < it < it_ref                         # Jacobi iterations after the hand-over
+    assert float((x - x_ref).abs().max() / x_ref.abs().max()) < 1e-8
