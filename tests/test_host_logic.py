@@ -97,3 +97,84 @@ def test_solver_interface_shape():
     assert s.tol == 1e-8 and hasattr(s, "maxiter") and callable(s.solve)
     s = b2.B200PCG(tol=1e-10, maxiter=123)
     assert s._get_atol(np.array([3.0, 4.0])) == pytest.approx(5e-10)
+
+
+def test_iterative_props_follow_the_dependency_graph():
+    # openpnm/algorithms/_algorithm.py:38-67: everything downstream of the quantity
+    # (and of settings.variable_props), lexicographic topological order, quantity excluded
+    pn = b2.Cubic([3, 3, 3])
+    ph = b2.Phase(pn)
+    ph.add_model(propname="pore.diffusivity", model=lambda t, c: 1.0, c="pore.concentration")
+    ph.add_model(propname="throat.diffusive_conductance", model=lambda t, D: 1.0,
+                 D="pore.diffusivity")
+    ph.add_model(propname="pore.rxn", model="standard_kinetics", prefactor="pore.A",
+                 exponent="pore.k", X="pore.concentration")
+    ph.add_model(propname="pore.unrelated", model=lambda t, v: 1.0, v="pore.viscosity")
+    alg = b2.ReactiveTransport(network=pn, phase=ph)
+    alg.settings._update({"quantity": "pore.concentration",
+                          "conductance": "throat.diffusive_conductance"})
+    assert alg.iterative_props == ["pore.diffusivity", "pore.rxn", "throat.diffusive_conductance"]
+    alg.settings["variable_props"] = {"pore.viscosity"}
+    assert alg.iterative_props == ["pore.diffusivity", "pore.rxn", "pore.viscosity",
+                                   "pore.unrelated", "throat.diffusive_conductance"]
+    # a plain Transport on a phase without models iterates nothing
+    assert b2.ReactiveTransport(network=pn, phase=b2.Phase(pn)).iterative_props == []
+
+
+def test_update_hook_only_when_python_models_are_involved():
+    pn = b2.Cubic([3, 3, 3])
+    ph = b2.Phase(pn)
+    ph["throat.diffusive_conductance"] = 1.0
+    ph["pore.A1"], ph["pore.A2"] = -1.0, 2.0
+    ph.add_model(propname="pore.rxn", model="power_law", A1="pore.A1", A2="pore.A2",
+                 X="pore.concentration")
+    alg = b2.ReactiveTransport(network=pn, phase=ph)
+    alg.settings._update({"quantity": "pore.concentration",
+                          "conductance": "throat.diffusive_conductance"})
+    alg.set_source(pores=[13], propname="pore.rxn")
+    assert alg._update_hook(None) is None                 # device kernel for the source
+    # a parameter array that itself depends on the quantity needs the host
+    ph.add_model(propname="pore.A1", model=lambda t, c: -1.0, c="pore.concentration")
+    assert alg._update_hook(None) is not None
+    del ph.models["pore.A1"]
+    # a Python source model, and a conductance that follows the quantity
+    ph.add_model(propname="pore.custom", model=lambda t, X: {"S1": 0, "S2": 0, "rate": 0},
+                 X="pore.concentration")
+    alg.set_source(pores=[14], propname="pore.custom")
+    assert alg._update_hook(None) is not None
+    alg.set_source(pores=[14], propname="pore.custom", mode="clear")
+    alg.pop("pore.source.custom")
+    assert alg._update_hook(None) is None
+    ph.add_model(propname="throat.diffusive_conductance", model=lambda t, c: 1.0,
+                 c="pore.concentration")
+    assert alg._update_hook(None) is not None
+
+
+def test_phase_regenerate_models_and_container_rules():
+    pn = b2.Cubic([2, 2, 2])
+    ph = b2.Phase(pn)
+    ph["pore.x"] = 2.0
+    ph.add_model(propname="pore.y", model=lambda t, x: t[x] ** 2, x="pore.x")
+    ph.add_model(propname="pore.src", model=lambda t, y: {"S1": t[y], "S2": 1.0, "rate": 0.0},
+                 y="pore.y")
+    ph.add_model(propname="pore.kernel", model="linear", X="pore.x")      # device kernel: skipped
+    ph.regenerate_models()
+    assert np.all(ph["pore.y"] == 4.0) and np.all(ph["pore.src.S1"] == 4.0)
+    assert set(ph["pore.src"].keys()) == {"S1", "S2", "rate"} and "pore.kernel" not in ph
+    ph["pore.x"] = 3.0
+    ph.regenerate_models(propnames=["pore.y"])
+    assert np.all(ph["pore.y"] == 9.0) and np.all(ph["pore.src.S1"] == 4.0)
+    assert pn.num_pores("left") == 4 and pn.num_throats() == pn.Nt
+    alg = b2.ReactiveTransport(network=pn, phase=ph)
+    alg["pore.source.a"] = True
+    alg["pore.source.b"] = False
+    assert set(alg.pop("pore.source").keys()) == {"a", "b"} and alg["pore.source"] == {}
+    assert alg.pop("pore.source", None) is None
+    with pytest.raises(KeyError):
+        alg.pop("pore.nothing")
+
+
+def test_b200pcg_precond_option():
+    assert b2.B200PCG(precond="amg").precond == "amg"
+    with pytest.raises(ValueError):
+        b2.B200PCG(precond="ilu")
