@@ -23,7 +23,9 @@
 //     everywhere: ||b - A x||_2 <= max(rtol ||b||_2, atol), confirmed with an
 //     explicitly recomputed residual.
 // Single GPU, symmetric systems; anything else stays with Jacobi-PCG / BiCGStab.
-#include <algorithm>
+// Environment knobs for experiments: B200_AMG_KLEVELS (0..3, default 2),
+// B200_AMG_F32=0 (fp64 coarse products), B200_AMG_MAXITER (solver.cu: iteration cap
+// before the hand-over to Jacobi-PCG, default 300).
 #include <math.h>
 #include <stdlib.h>
 #include <time.h>
@@ -71,7 +73,6 @@ struct AmgState {
   // level 0 lives in the Jacobi-scaled, padded layout of the PCG operator
   DevBuf z0, z1, ax0, dir0, winv, fd, fq;
   DevBuf lmax_dev;
-  int64_t vlen = 0;
 };
 
 // tuning knob for experiments (B200_AMG_KLEVELS=0..3): levels whose coarse problem
