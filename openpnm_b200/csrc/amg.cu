@@ -5,7 +5,7 @@
 // lattice (3256 at 400^3); this needs ~30 at any size.
 //
 // Algorithm (plain aggregation + K-cycle, after Notay's AGMG, restated for the GPU):
-//   setup, per level: three passes of pairwise matching by handshaking -- every
+//   setup, per level: three passes (four on the fine level) of pairwise matching by handshaking -- every
 //     unmatched row proposes to its strongest unmatched neighbour (largest -a_ij,
 //     smaller index on ties), mutual proposals match; leftovers join the
 //     aggregate of their strongest matched neighbour; rows without negative
@@ -24,6 +24,7 @@
 //     explicitly recomputed residual.
 // Single GPU, symmetric systems; anything else stays with Jacobi-PCG / BiCGStab.
 // Environment knobs for experiments: B200_AMG_KLEVELS (0..3, default 2),
+// B200_AMG_PASSES0 (pairwise passes on the fine level, default 4),
 // B200_AMG_F32=0 (fp64 coarse products), B200_AMG_MAXITER (solver.cu: iteration cap
 // before the hand-over to Jacobi-PCG, default 300).
 #include <math.h>
@@ -86,6 +87,20 @@ static int amg_klevels() {
   return k;
 }
 #define AMG_KLEVELS amg_klevels()
+
+// pairwise passes on the fine level (B200_AMG_PASSES0=1..6): the fine level runs
+// at 85 % of the HBM peak on its DIA operator, the coarse CSR levels at ~40 %, so
+// the first coarsening is one pass more aggressive than the others -- a few more
+// iterations, half the coarse-level work
+#define AMG_PASSES0_DEFAULT 4
+static int amg_passes0() {
+  static int k = -1;
+  if (k < 0) {
+    const char* e = getenv("B200_AMG_PASSES0");
+    k = (e && e[0] >= '1' && e[0] <= '6') ? e[0] - '0' : AMG_PASSES0_DEFAULT;
+  }
+  return k;
+}
 
 // B200_AMG_F32=0 keeps the coarse operators in fp64 (A/B experiments)
 static bool amg_f32() {
@@ -819,11 +834,12 @@ static int amg_setup(b200_ctx* ctx) {
     lvl.indices = A->lv[l + 1].indices;
     lvl.data = A->lv[l + 1].data;
     lvl.dinv = A->lv[l + 1].dinv;
-    for (int pass = 0; pass < AMG_PASSES; ++pass) {
-      CsrOut& dst = (pass == AMG_PASSES - 1) ? lvl : A->t_csr[pass & 1];
+    const int npass = (l == 0) ? amg_passes0() : AMG_PASSES;
+    for (int pass = 0; pass < npass; ++pass) {
+      CsrOut& dst = (pass == npass - 1) ? lvl : A->t_csr[pass & 1];
       DevBuf& aggp = (pass == 0) ? A->lv[l].agg : A->t_aggpass;
       int rc = amg_pair_pass(ctx, A, (int)nn, ip, ix, av, dg, aggp, dst);
-      if (pass == AMG_PASSES - 1) {                      // hand the (possibly regrown) buffers back
+      if (pass == npass - 1) {                           // hand the (possibly regrown) buffers back
         A->lv[l + 1].indptr = lvl.indptr;
         A->lv[l + 1].indices = lvl.indices;
         A->lv[l + 1].data = lvl.data;

@@ -59,7 +59,7 @@ def galerkin(A, agg):
 class Level: pass
 
 
-def setup(A, passes=3, coarsest=2000, max_levels=10):
+def setup(A, passes=3, coarsest=2000, max_levels=10, passes0=None):
     levels = []
     while True:
         L = Level(); L.A = A.tocsr(); L.n = A.shape[0]
@@ -69,7 +69,7 @@ def setup(A, passes=3, coarsest=2000, max_levels=10):
         if L.n <= coarsest or len(levels) >= max_levels:
             break
         agg = np.arange(L.n); Ac = L.A
-        for _ in range(passes):
+        for _ in range(passes0 if (passes0 and len(levels) == 1) else passes):
             a = pair_pass(Ac)
             _, Ac = galerkin(Ac, a)
             agg = np.where(agg >= 0, a[np.maximum(agg, 0)], -1)
@@ -122,7 +122,8 @@ def cycle(levels, l, b, prm):
     VIS[l] = VIS.get(l, 0) + 1
     if l == len(levels) - 1:
         return coarse_cg(L, b, prm['crtol'], prm['cmax'])
-    x = cheb(L, b, None, True, prm.get('pre', prm['deg']), prm['ratio'])
+    dg = prm['deg'] if l == 0 else prm.get('cdeg', prm['deg'])
+    x = cheb(L, b, None, True, prm.get('pre', dg), prm['ratio'])
     rc = L.P.T @ (b - L.A @ x)
     Lc = levels[l + 1]
     if l < prm['klev'] and l + 1 < len(levels) - 1:
@@ -136,7 +137,7 @@ def cycle(levels, l, b, prm):
     else:
         ec = cycle(levels, l + 1, rc, prm)
     x = x + L.P @ ec
-    return cheb(L, b, x, False, prm.get('post', prm['deg']), prm['ratio'])
+    return cheb(L, b, x, False, prm.get('post', dg), prm['ratio'])
 
 
 def fcg(A, b, M, rtol=1e-10, maxiter=300):
@@ -174,7 +175,10 @@ def main():
     passes = int(sys.argv[8]) if len(sys.argv) > 8 else 3
     if len(sys.argv) > 10: prm['pre'] = int(sys.argv[9]); prm['post'] = int(sys.argv[10])
     A, b = problem(kind, N)
-    t0 = time.time(); levels = setup(A, passes=passes)
+    import os
+    p0 = int(os.environ.get('P0', '0')) or None
+    if os.environ.get('CDEG'): prm['cdeg'] = int(os.environ['CDEG'])
+    t0 = time.time(); levels = setup(A, passes=passes, passes0=p0)
     print('levels', [L.n for L in levels], 'nnz', [L.A.nnz for L in levels], 'lmax', ['%.2f' % L.lmax for L in levels], 'setup %.1fs' % (time.time() - t0))
     t0 = time.time()
     x, it = fcg(A, b, lambda r: cycle(levels, 0, r, prm))
