@@ -358,7 +358,11 @@ def gpu_arm(args):
     # the hierarchy, solve to the same rtol -- time-to-solve is the metric here,
     # an AMG iteration is not comparable to a PCG iteration
     amg = None
-    if world == 1 and not args.no_amg:
+    # (several GPUs: the block-wise slab multigrid is experimental and slower than
+    # Jacobi-PCG so far -- opt-in with --amg-multi, which also sets B200_AMG_SLABS=1)
+    if args.amg_multi:
+        os.environ["B200_AMG_SLABS"] = "1"
+    if not args.no_amg and (world == 1 or args.amg_multi):
         ctx.set_precond("amg")
         try:
             device_step()                               # warm-up (allocates the hierarchy)
@@ -371,15 +375,22 @@ def gpu_arm(args):
                     sta = ctx.stats()
                 a1.record()
             barrier()
-            ms_amg = a0.elapsed_time(a1) / args.steps
+            t_amg = torch.tensor([a0.elapsed_time(a1) / args.steps], dtype=torch.float64,
+                                 device=ctx.tdev)
+            if world > 1:
+                dist.all_reduce(t_amg, op=dist.ReduceOp.MAX)
+            ms_amg = float(t_amg.item())
             dx = float((xa - x).abs().max() / x.abs().max())
             amg = {"time_to_solve_s": ms_amg * 1e-3, "iters": int(ita), "relres": rela,
                    "info": int(infoa), "hierarchy_setup_ms": sta["t_setup_ms"],
-                   "solve_ms": sta["t_solve_ms"], "levels": ctx.amg_setup(),
+                   "solve_ms": sta["t_solve_ms"],
+                   "levels": ctx.amg_setup() if world == 1 else "one hierarchy per rank",
                    "max_rel_diff_vs_jacobi_pcg": dx,
                    "speedup_vs_jacobi_pcg": ms_step / ms_amg,
                    "what": "B200PCG(precond='amg'): aggregation-AMG K-cycle + flexible CG "
-                           "(csrc/amg.cu); step = assembly + hierarchy build + solve"}
+                           "(csrc/amg.cu); step = assembly + hierarchy build + solve"
+                           + ("" if world == 1 else "; slabs: global FCG over NCCL, every rank "
+                              "preconditions with the hierarchy of its own block")}
             del xa
         finally:
             ctx.set_precond("jacobi")
@@ -534,6 +545,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-p2p", action="store_true")
     ap.add_argument("--no-amg", action="store_true")
+    ap.add_argument("--amg-multi", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

@@ -166,7 +166,9 @@ int b200_pcg_format(b200_ctx* ctx, int* fmt, int* ndiags);
  * ~30 iterations at any size instead of O(N) for an N^3 lattice.  Same
  * stopping rule, same outputs (`iters` counts outer FCG iterations).  Applies
  * to symmetric single-GPU systems with more than 2048 rows; otherwise, and for
- * matrices that cannot be coarsened, the call silently stays with Jacobi.
+ * matrices that cannot be coarsened, the call silently stays with Jacobi
+ * (slab runs too, unless B200_AMG_SLABS=1 selects the experimental block-wise
+ * variant).
  * b200_amg_setup builds the hierarchy now (it is otherwise built by the first
  * solve after the matrix changed); the two accessors export a level's CSR
  * (level 0 = the system matrix) and its aggregation map (row -> coarse row, -1

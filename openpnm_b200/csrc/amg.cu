@@ -22,7 +22,9 @@
 //     kernel of solver.cu does every fine-level product), stopping rule as
 //     everywhere: ||b - A x||_2 <= max(rtol ||b||_2, atol), confirmed with an
 //     explicitly recomputed residual.
-// Single GPU, symmetric systems; anything else stays with Jacobi-PCG / BiCGStab.
+// Symmetric systems on one GPU.  On slabs (several GPUs) an experimental opt-in mode
+// (B200_AMG_SLABS=1) lets every rank precondition with the hierarchy of its own block
+// (additive Schwarz); by default, and for anything else, Jacobi-PCG / BiCGStab.
 // Environment knobs for experiments: B200_AMG_KLEVELS (0..3, default 2),
 // B200_AMG_PASSES0 (pairwise passes on the fine level, default 4),
 // B200_AMG_F32=0 (fp64 coarse products), B200_AMG_MAXITER (solver.cu: iteration cap
@@ -137,9 +139,12 @@ void b200_amg_release(b200_ctx* ctx) {
 // ================================================================== matching
 // one thread per row; CSR columns ascending, so the first maximum is the
 // smallest index among equal weights
+// (shift: columns are global ids in a slab; entries that point outside the owned
+// rows [shift, shift + n) are not part of this rank's hierarchy)
 __global__ void __launch_bounds__(AMG_T) k_amg_propose(const int* __restrict__ ip,
                                                        const int* __restrict__ ix,
                                                        const double* __restrict__ av, int n,
+                                                       int shift,
                                                        const int* __restrict__ match,
                                                        int* __restrict__ prop) {
   const int stride = gridDim.x * blockDim.x;
@@ -148,8 +153,9 @@ __global__ void __launch_bounds__(AMG_T) k_amg_propose(const int* __restrict__ i
     if (match[i] < 0) {
       double bw = 0.0;
       for (int e = ip[i]; e < ip[i + 1]; ++e) {
-        const int j = ix[e];
+        const int j = ix[e] - shift;
         const double w = -av[e];
+        if (j < 0 || j >= n) continue;
         if (j == i || !(w > bw) || match[j] >= 0) continue;
         bw = w;
         best = j;
@@ -174,6 +180,7 @@ __global__ void __launch_bounds__(AMG_T) k_amg_accept(int n, const int* __restri
 __global__ void __launch_bounds__(AMG_T) k_amg_leader(const int* __restrict__ ip,
                                                       const int* __restrict__ ix,
                                                       const double* __restrict__ av, int n,
+                                                      int shift,
                                                       const int* __restrict__ match,
                                                       int* __restrict__ leader,
                                                       int* __restrict__ flag) {
@@ -187,8 +194,9 @@ __global__ void __launch_bounds__(AMG_T) k_amg_leader(const int* __restrict__ ip
       int best = -1, deg = 0;
       double bw = 0.0;
       for (int e = ip[i]; e < ip[i + 1]; ++e) {
-        const int j = ix[e];
+        const int j = ix[e] - shift;
         const double w = -av[e];
+        if (j < 0 || j >= n) continue;
         if (j == i || !(w > 0.0)) continue;
         ++deg;
         if (match[j] < 0 || !(w > bw)) continue;
@@ -292,7 +300,8 @@ __global__ void __launch_bounds__(128) k_amg_row_build(int nc, const int* __rest
                                                        const int* __restrict__ ix,
                                                        const double* __restrict__ av,
                                                        const double* __restrict__ diag,
-                                                       const int* __restrict__ agg,
+                                                       const int* __restrict__ agg, int shift,
+                                                       int nf,
                                                        const int* __restrict__ tofs,
                                                        int* __restrict__ tc,
                                                        double* __restrict__ tv,
@@ -307,7 +316,8 @@ __global__ void __launch_bounds__(128) k_amg_row_build(int nc, const int* __rest
     for (int q = cptr[I]; q < cptr[I + 1]; ++q) {
       const int i = cmem[q];
       for (int e = ip[i]; e < ip[i + 1]; ++e) {
-        const int j = ix[e];
+        const int j = ix[e] - shift;
+        if (j < 0 || j >= nf) continue;
         const int a = agg[j];
         if (a < 0) continue;
         const double v = (diag != nullptr && j == i) ? diag[i] : av[e];
@@ -360,6 +370,7 @@ __global__ void __launch_bounds__(AMG_T) k_amg_rowbound(const int* __restrict__ 
                                                         const int* __restrict__ ix,
                                                         const double* __restrict__ av,
                                                         const double* __restrict__ diag, int n,
+                                                        int shift,
                                                         unsigned long long* __restrict__ out) {
   const int stride = gridDim.x * blockDim.x;
   double mx = 0.0;
@@ -367,7 +378,7 @@ __global__ void __launch_bounds__(AMG_T) k_amg_rowbound(const int* __restrict__ 
     double s = 0.0, d = diag ? diag[i] : 0.0;
     for (int e = ip[i]; e < ip[i + 1]; ++e) {
       const double v = av[e];
-      if (ix[e] == i) {
+      if (ix[e] - shift == i) {
         if (!diag) d = v;
         s += fabs(diag ? diag[i] : v);
       } else {
@@ -732,7 +743,8 @@ static int amg_members(b200_ctx* ctx, AmgState* A, int n, int nc, const int* agg
 
 // one pairwise pass on (n, ip, ix, av [, diag]) -> agg (n) and the Galerkin matrix
 static int amg_pair_pass(b200_ctx* ctx, AmgState* A, int n, const int* ip, const int* ix,
-                         const double* av, const double* diag, DevBuf& agg_out, CsrOut& out) {
+                         const double* av, const double* diag, int shift, DevBuf& agg_out,
+                         CsrOut& out) {
   DevBuf& match = A->t_match;
   DevBuf& prop = A->t_prop;
   DevBuf& ids = A->t_ids;
@@ -743,11 +755,12 @@ static int amg_pair_pass(b200_ctx* ctx, AmgState* A, int n, const int* ip, const
   CK(cudaMemsetAsync(match.p, 0xff, (size_t)n * sizeof(int), ctx->stream));
   const int g = grid_for(n, AMG_T);
   for (int r = 0; r < AMG_ROUNDS; ++r) {
-    LAUNCH(ctx, k_amg_propose, g, AMG_T, 0, ip, ix, av, n, match.as<int>(), prop.as<int>());
+    LAUNCH(ctx, k_amg_propose, g, AMG_T, 0, ip, ix, av, n, shift, match.as<int>(),
+           prop.as<int>());
     LAUNCH(ctx, k_amg_accept, g, AMG_T, 0, n, prop.as<int>(), match.as<int>());
   }
   // prop <- leader, ids <- flags -> scanned ids
-  LAUNCH(ctx, k_amg_leader, g, AMG_T, 0, ip, ix, av, n, match.as<int>(), prop.as<int>(),
+  LAUNCH(ctx, k_amg_leader, g, AMG_T, 0, ip, ix, av, n, shift, match.as<int>(), prop.as<int>(),
          ids.as<int>());
   int64_t nc64 = 0;
   RET(b200_scan_exclusive_i32(ctx, ids.as<int>(), ids.as<int>(), n, &nc64));
@@ -767,7 +780,7 @@ static int amg_pair_pass(b200_ctx* ctx, AmgState* A, int n, const int* ip, const
   CK(A->t_tc.ensure((size_t)(T > 0 ? T : 1) * sizeof(int)));
   CK(A->t_tv.ensure((size_t)(T > 0 ? T : 1) * sizeof(double)));
   LAUNCH(ctx, k_amg_row_build, gc, 128, 0, nc, cptr, cmem, ip, ix, av, diag, agg_out.as<int>(),
-         ids.as<int>(), A->t_tc.as<int>(), A->t_tv.as<double>(), match.as<int>());
+         shift, n, ids.as<int>(), A->t_tc.as<int>(), A->t_tv.as<double>(), match.as<int>());
   CK(out.indptr.ensure((size_t)(nc + 1) * sizeof(int)));
   int64_t cnnz = 0;
   RET(b200_scan_exclusive_i32(ctx, match.as<int>(), out.indptr.as<int>(), nc, &cnnz));
@@ -782,11 +795,12 @@ static int amg_pair_pass(b200_ctx* ctx, AmgState* A, int n, const int* ip, const
   return B200_OK;
 }
 
-static int amg_level_bound(b200_ctx* ctx, AmgState* A, AmgLevel& L, const double* diag) {
+static int amg_level_bound(b200_ctx* ctx, AmgState* A, AmgLevel& L, const double* diag,
+                           int shift) {
   CK(A->lmax_dev.ensure(sizeof(unsigned long long)));
   CK(cudaMemsetAsync(A->lmax_dev.p, 0, sizeof(unsigned long long), ctx->stream));
   LAUNCH(ctx, k_amg_rowbound, grid_for(L.n, AMG_T), AMG_T, 0, L.ip, L.ix, L.av, diag, (int)L.n,
-         A->lmax_dev.as<unsigned long long>());
+         shift, A->lmax_dev.as<unsigned long long>());
   double lm = 0.0;
   CK(cudaMemcpyAsync(&lm, A->lmax_dev.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -809,7 +823,7 @@ static int amg_setup(b200_ctx* ctx) {
     L.ip = ctx->sys_indptr.as<int>();
     L.ix = ctx->sys_indices.as<int>();
     L.av = ctx->sys_data.as<double>();
-    RET(amg_level_bound(ctx, A, L, diag0));
+    RET(amg_level_bound(ctx, A, L, diag0, (int)ctx->row_begin));
   }
   size_t l = 0;
   double t_prev = 0.0;
@@ -838,7 +852,8 @@ static int amg_setup(b200_ctx* ctx) {
     for (int pass = 0; pass < npass; ++pass) {
       CsrOut& dst = (pass == npass - 1) ? lvl : A->t_csr[pass & 1];
       DevBuf& aggp = (pass == 0) ? A->lv[l].agg : A->t_aggpass;
-      int rc = amg_pair_pass(ctx, A, (int)nn, ip, ix, av, dg, aggp, dst);
+      const int shift = (l == 0 && pass == 0) ? (int)ctx->row_begin : 0;
+      int rc = amg_pair_pass(ctx, A, (int)nn, ip, ix, av, dg, shift, aggp, dst);
       if (pass == npass - 1) {                           // hand the (possibly regrown) buffers back
         A->lv[l + 1].indptr = lvl.indptr;
         A->lv[l + 1].indices = lvl.indices;
@@ -873,7 +888,7 @@ static int amg_setup(b200_ctx* ctx) {
     C.ip = C.indptr.as<int>();
     C.ix = C.indices.as<int>();
     C.av = C.data.as<double>();
-    RET(amg_level_bound(ctx, A, C, nullptr));
+    RET(amg_level_bound(ctx, A, C, nullptr, 0));
     if (amg_f32()) {
       CK(C.dataf.ensure((size_t)(C.nnz > 0 ? C.nnz : 1) * sizeof(float)));
       LAUNCH(ctx, k_amg_to_f32, grid_for(C.nnz, AMG_T), AMG_T, 0, C.nnz, C.av, C.dataf.as<float>());
@@ -1015,9 +1030,18 @@ static int amg_child(b200_ctx* ctx, AmgState* A, size_t l) {
 }
 
 // ================================================================ outer solver
+// (both settings are the same on every rank of a slab run; everything that can
+// differ between ranks is agreed on collectively inside b200_amg_pcg).  On slabs the
+// block-wise multigrid is correct but not competitive yet -- without coarse levels
+// that span the ranks the slab interfaces cost ~4x the iterations (129 vs 35 on two
+// slabs of a 48x24x24 lattice; 200^3 on two GPUs: 258 ms against 213 ms for
+// Jacobi-PCG and 93 ms on one GPU) -- so it is opt-in (B200_AMG_SLABS=1) and slab
+// runs stay with Jacobi-PCG by default.
 bool b200_amg_applicable(b200_ctx* ctx) {
-  return ctx->precond == B200_PRECOND_AMG && !ctx->nonsym && ctx->nranks == 1 &&
-         ctx->n > AMG_COARSEST && ctx->n < (1ll << 31);
+  if (ctx->precond != B200_PRECOND_AMG || ctx->nonsym) return false;
+  if (ctx->nranks == 1) return true;
+  const char* e = getenv("B200_AMG_SLABS");
+  return e && e[0] == '1';
 }
 
 // returns B200_OK with *used = 0 when the hierarchy could not be built (coarsening
@@ -1025,15 +1049,32 @@ bool b200_amg_applicable(b200_ctx* ctx) {
 int b200_amg_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol, int64_t maxiter,
                  double* x, int64_t* iters, double* relres, int* info, int* used) {
   *used = 0;
+  // Slab mode (one rank per GPU): the outer flexible CG runs on the global operator
+  // (halo exchange + all-reduced dot products, as in the PCG) and every rank uses the
+  // hierarchy of the rows and columns it owns as its preconditioner -- additive
+  // Schwarz without overlap, no communication inside a cycle (the cycle's operands
+  // have zero halo pads, so its fine-level products see the local block only).
+  const bool multi = ctx->nranks > 1;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   RET(b200_pcg_prepare(ctx, ctx->force_fmt));
-  if (!ctx->unit_diag) return B200_OK;
+  // every rank must take the same path: agree on the local verdicts
+  int64_t bad = (!ctx->unit_diag || ctx->n <= AMG_COARSEST || ctx->n >= (1ll << 31)) ? 1 : 0;
+  RET(b200_allreduce_max_host(ctx, &bad));
+  if (bad) return B200_OK;
   AmgState* A = amg_of(ctx);
   // a re-linearised source term moves the diagonal: coarse operators built from the
   // old one precondition badly (config 5: 250 instead of 31 iterations), so rebuild
-  if (A->epoch != ctx->sys_epoch || A->lin_epoch != ctx->lin_epoch || A->nlev == 0)
-    RET(amg_setup(ctx));
-  if (!A->valid) return B200_OK;
+  if (A->epoch != ctx->sys_epoch || A->lin_epoch != ctx->lin_epoch || A->nlev == 0) {
+    const int rc = amg_setup(ctx);
+    if (rc != B200_OK) {
+      if (!multi) return rc;
+      A->valid = false;          // reported below as "no hierarchy": all ranks use Jacobi
+      A->nlev = 0;
+    }
+  }
+  bad = A->valid ? 0 : 1;
+  RET(b200_allreduce_max_host(ctx, &bad));
+  if (bad) return B200_OK;
   *used = 1;
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   const int64_t n = ctx->n, pad = ctx->pad;
@@ -1067,14 +1108,20 @@ int b200_amg_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol, int6
   CK(cudaMemsetAsync(flags, 0, FLAG_COUNT * sizeof(int), ctx->stream));
   CK(cudaMemsetAsync(sc, 0, SC_COUNT * sizeof(double), ctx->stream));
   RET(b200_launch_init(ctx, x0, xt, bt, sc + SC_BNORM));
+  if (multi) {
+    RET(b200_allreduce_sum(ctx, sc + SC_BNORM, 1));
+    RET(b200_halo_exchange(ctx, ctx->vx.as<double>()));
+  }
   RET(b200_spmv_dots(ctx, xt, bt, v, sc + SC_AUX0));
   RET(b200_launch_resid(ctx, bt, v, diag, r, tmp, sc + F_RR, sc + F_TRUE));
+  if (multi) RET(b200_allreduce_sum(ctx, sc + F_RR, 2));
   CK(cudaMemcpyAsync(ctx->scal_h, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost,
                      ctx->stream));
   CK(cudaMemcpyAsync(ctx->flags_h, flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost,
                      ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  if (ctx->flags_h[FLAG_NONFINITE] || !isfinite(ctx->scal_h[SC_BNORM]) ||
+  // in slab mode judge by the all-reduced norms only (same verdict on every rank)
+  if ((!multi && ctx->flags_h[FLAG_NONFINITE]) || !isfinite(ctx->scal_h[SC_BNORM]) ||
       !isfinite(ctx->scal_h[F_TRUE]))
     FAIL(B200_ERR_NONFINITE, "b or x0 contains inf/nan values");
   const double bnorm2 = ctx->scal_h[SC_BNORM];
@@ -1102,10 +1149,17 @@ int b200_amg_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol, int6
       RET(amg_cycle(ctx, A, 0, r, z, ax0, dir0));
       if (!first) LAUNCH(ctx, k_amg_dot1, g, AMG_T, 0, n, z, q, part, ticket, fs + F_ZQ);
     }
+    if (multi && !first) RET(b200_allreduce_sum(ctx, fs + F_ZQ, 1));
     LAUNCH(ctx, k_amg_fcg_dir, g, AMG_T, 0, n, z, r, d, first ? 1 : 0, fs, part, ticket,
            fs + F_DR);
+    if (multi) {
+      RET(b200_allreduce_sum(ctx, fs + F_DR, 1));
+      RET(b200_halo_exchange(ctx, A->fd.as<double>()));
+    }
     RET(b200_spmv_dots(ctx, d, r, q, fs + F_DQ));          // fs[F_DQ] = d.q
+    if (multi) RET(b200_allreduce_sum(ctx, fs + F_DQ, 3));
     LAUNCH(ctx, k_amg_fcg_update, g, AMG_T, 0, n, xt, r, d, q, diag, fs, part, ticket, fs);
+    if (multi) RET(b200_allreduce_sum(ctx, fs + F_RR, 2));
     CK(cudaMemcpyAsync(ctx->scal_h, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost,
                        ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1119,8 +1173,10 @@ int b200_amg_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol, int6
     if (!isfinite(true2) || !isfinite(dq)) { inf = -1; break; }
     if (!(dq > 0.0)) { inf = -1; break; }
     if (true2 <= tol2) {
+      if (multi) RET(b200_halo_exchange(ctx, ctx->vx.as<double>()));
       RET(b200_spmv_dots(ctx, xt, bt, v, sc + SC_AUX0));
       RET(b200_launch_resid(ctx, bt, v, diag, r, tmp, sc + F_RR, sc + F_TRUE));
+      if (multi) RET(b200_allreduce_sum(ctx, sc + F_RR, 2));
       CK(cudaMemcpyAsync(ctx->scal_h, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost,
                          ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));

@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(PCG_T) k_dia_smooth(DiaPack A, int mode,
 }
 
 bool b200_dia_smooth_available(b200_ctx* ctx) {
-  return ctx->fmt == B200_FMT_DIA && ctx->unit_diag && ctx->nranks == 1;
+  return ctx->fmt == B200_FMT_DIA && ctx->unit_diag;
 }
 
 int b200_dia_smooth(b200_ctx* ctx, int mode, const double* p_owned, const double* b_owned,
