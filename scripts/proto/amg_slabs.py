@@ -4,12 +4,14 @@ boundary (matching ignores cross-slab edges), the Galerkin operators stay GLOBAL
 multigrid for the whole problem and every level can be row-partitioned by slab.
 Question answered here: what does forbidding cross-slab aggregates cost in
 iterations?  Not product code."""
+import os
 import sys
 import numpy as np, scipy.sparse as sp
-sys.path.insert(0, '/root/repo')
-src = open('/root/repo/scripts/proto/amg_v2.py').read().replace('\nmain()\n', '\n')
-ns = {}
-exec(compile(src, 'amgv2', 'exec'), ns)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import amg_v2
+ns = vars(amg_v2)
 from oracle import oracle
 
 
@@ -59,4 +61,5 @@ def main():
               'relres %.1e' % (np.linalg.norm(b - A @ x) / np.linalg.norm(b)), flush=True)
 
 
-main()
+if __name__ == '__main__':
+    main()

@@ -3,7 +3,8 @@ implements -- same matching rule, same Chebyshev recurrences, same truncated
 K-cycle, CG on the coarsest level.  Used to choose parameters; not product code."""
 import sys, time
 import numpy as np, scipy.sparse as sp
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import oracle
 
 ROUNDS = 5
@@ -186,4 +187,5 @@ def main():
           'relres %.2e' % (np.linalg.norm(b - A @ x) / np.linalg.norm(b)))
 
 
-main()
+if __name__ == '__main__':
+    main()

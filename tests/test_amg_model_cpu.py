@@ -1,0 +1,84 @@
+"""CPU: the numpy model of the multigrid preconditioner (scripts/proto/amg_v2.py,
+amg_slabs.py) -- the design evidence behind csrc/amg.cu, kept executable:
+
+* ~30 outer iterations whatever the lattice size (Jacobi-PCG grows with N);
+* the hierarchy must be built on the UNSCALED operator: a piecewise-constant P on
+  the Jacobi-scaled one (near-null-space D^1/2 1, not 1) loses the coarse correction;
+* aggregates that never cross a slab boundary cost nothing when the Galerkin
+  operators stay global (the round-2 multi-GPU design), whereas block-wise
+  hierarchies (additive Schwarz, the experimental B200_AMG_SLABS mode) do.
+
+Nothing here is product code and nothing under openpnm_b200/ imports it."""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "scripts", "proto"))
+import amg_slabs  # noqa: E402
+import amg_v2  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+PRM = dict(deg=2, ratio=8.0, klev=2, crtol=0.1, cmax=30)
+
+
+def problem(shape, seed=3):
+    net = oracle.cubic_network(shape)
+    Np = net["Np"]
+    g = 10.0 ** np.random.default_rng(seed).uniform(-15, -12, net["Nt"])
+    bcv = np.full(Np, np.nan)
+    bcv[net["labels"]["left"]] = 2.0
+    bcv[net["labels"]["right"]] = 1.0
+    A, b, _ = oracle.apply_bcs(oracle.build_A(net["conns"], g, Np), Np, bcv, None)
+    return oracle.to_csr(A, Np), b
+
+
+def solve(A, b, levels):
+    x, it = amg_v2.fcg(A, b, lambda r: amg_v2.cycle(levels, 0, r, PRM), rtol=1e-10)
+    assert np.linalg.norm(b - A @ x) <= 1e-10 * np.linalg.norm(b)
+    return it
+
+
+def test_iterations_do_not_grow_with_the_lattice():
+    its = {}
+    for n in (16, 24, 32):
+        A, b = problem((n, n, n))
+        its[n] = solve(A, b, amg_v2.setup(A, passes=3, passes0=4, coarsest=500))
+    xj, _info, itj = oracle.jacobi_pcg(*problem((32, 32, 32)), rtol=1e-10, maxiter=5000)
+    assert max(its.values()) <= 45 and its[32] <= its[16] + 8, its
+    assert itj > 4 * its[32]
+
+
+def test_hierarchy_must_be_built_on_the_unscaled_operator():
+    A, b = problem((24, 24, 24))
+    good = solve(A, b, amg_v2.setup(A, passes=3, passes0=4, coarsest=500))
+    s = 1.0 / np.sqrt(A.diagonal())
+    At = (sp.diags(s) @ A @ sp.diags(s)).tocsr()
+    bad = solve(At, s * b, amg_v2.setup(At, passes=3, passes0=4, coarsest=500))
+    assert bad > 1.5 * good, (good, bad)
+
+
+def test_slab_respecting_aggregates_cost_nothing_but_blockwise_hierarchies_do():
+    shape = (32, 12, 12)
+    A, b = problem(shape)
+    Np = A.shape[0]
+    plane = shape[1] * shape[2]
+    base = solve(A, b, amg_v2.setup(A, passes=3, passes0=4, coarsest=500))
+    for world in (2, 4):
+        owner = (np.arange(Np) // plane) * world // shape[0]
+        it = solve(A, b, amg_slabs.setup_slabs(A, owner, coarsest=500))
+        assert it <= base + 4, (world, base, it)
+    # block-wise: every slab its own hierarchy, no coupling between them in M
+    cuts = np.linspace(0, shape[0], 3).astype(int) * plane
+    hier = [amg_v2.setup(A[a:c, a:c].tocsr(), passes=3, passes0=4, coarsest=500)
+            for a, c in zip(cuts[:-1], cuts[1:])]
+
+    def M(r):
+        z = np.empty_like(r)
+        for (a, c), lv in zip(zip(cuts[:-1], cuts[1:]), hier):
+            z[a:c] = amg_v2.cycle(lv, 0, r[a:c], PRM)
+        return z
+    x, it_block = amg_v2.fcg(A, b, M, rtol=1e-10)
+    assert it_block > 2 * base, (base, it_block)
