@@ -6,14 +6,16 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
 import openpnm_b200 as b2
 from openpnm_b200 import dist as bdist
-from oracle import oracle
+from _gen import delaunay_conns
 
 
 def delaunay(npts):
     pts = np.random.default_rng(0).random((npts, 3))
-    c = oracle.delaunay_network(pts)
+    c = delaunay_conns(pts)
     L = np.linalg.norm(pts[c[:, 0]] - pts[c[:, 1]], axis=1)
     c = c[L < 4.0 * npts ** (-1 / 3)]
     perm, inv = bdist.coordinate_order(pts, axis=0)

@@ -1,9 +1,10 @@
-"""CPU prototype (numpy/scipy) of an aggregation AMG with K-cycle for the
+"""TEST INFRASTRUCTURE (uses oracle/), kept for the record: the first CPU prototype (numpy/scipy) of an aggregation AMG with K-cycle for the
 Jacobi-scaled graph Laplacian systems of the transport path: measures outer
 iteration counts before any CUDA is written.  Not product code."""
 import sys, time
 import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import oracle
 
 

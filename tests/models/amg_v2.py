@@ -1,4 +1,4 @@
-"""CPU model (numpy/scipy) of the aggregation-AMG K-cycle that csrc/amg.cu
+"""TEST INFRASTRUCTURE (uses oracle/): CPU model (numpy/scipy) of the aggregation-AMG K-cycle that csrc/amg.cu
 implements -- same matching rule, same Chebyshev recurrences, same truncated
 K-cycle, CG on the coarsest level.  Used to choose parameters; not product code."""
 import sys, time

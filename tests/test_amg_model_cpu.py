@@ -1,4 +1,4 @@
-"""CPU: the numpy model of the multigrid preconditioner (scripts/proto/amg_v2.py,
+"""CPU: the numpy model of the multigrid preconditioner (tests/models/amg_v2.py,
 amg_slabs.py) -- the design evidence behind csrc/amg.cu, kept executable:
 
 * ~30 outer iterations whatever the lattice size (Jacobi-PCG grows with N);
@@ -16,7 +16,7 @@ import numpy as np
 import scipy.sparse as sp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "scripts", "proto"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "models"))
 import amg_slabs  # noqa: E402
 import amg_v2  # noqa: E402
 from oracle import oracle  # noqa: E402
