@@ -82,3 +82,33 @@ def test_slab_respecting_aggregates_cost_nothing_but_blockwise_hierarchies_do():
         return z
     x, it_block = amg_v2.fcg(A, b, M, rtol=1e-10)
     assert it_block > 2 * base, (base, it_block)
+
+
+def test_distributed_setup_needs_only_the_halo_of_the_aggregation_map():
+    """The rank-by-rank construction of tests/models/amg_dist_model.py (owned-column
+    matching, one integer all-gather for the numbering, an index-list exchange of the
+    aggregation map at the slab interfaces, local Galerkin rows) reproduces the
+    global slab-respecting hierarchy level by level -- and so inherits its
+    iteration count."""
+    import amg_dist_model
+    shape = (32, 12, 12)
+    A, b = problem(shape)
+    Np = A.shape[0]
+    plane = shape[1] * shape[2]
+    for world in (2, 4):
+        offsets = (np.linspace(0, shape[0], world + 1).astype(int) * plane)
+        owner = np.searchsorted(offsets, np.arange(Np), side="right") - 1
+        ref = amg_slabs.setup_slabs(A, owner, coarsest=500)
+        levels, maps, traffic = amg_dist_model.build(A, offsets, coarsest=500)
+        assert len(levels) == len(ref)
+        for lv, L in zip(levels, ref):
+            G = amg_dist_model.assemble_global(lv)
+            assert G.shape == L.A.shape
+            D = (G - L.A).tocsr()
+            assert abs(D).max() <= 1e-12 * abs(L.A).max()
+        # the exchanged map entries are interface-sized, not volume-sized
+        assert max(max(t) for t in traffic[0]) <= 2 * plane
+        # the composite map of the fine level is the prolongation the global model uses
+        P = ref[0].P.tocsr()
+        k = maps[0] >= 0
+        assert np.array_equal(P.indices, maps[0][k]) and P.nnz == k.sum()
