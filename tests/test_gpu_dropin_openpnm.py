@@ -62,7 +62,10 @@ def test_reference_stokesflow_with_b200_multigrid(op, b2):
     sf.run(solver=solver)
     assert sf.soln.is_converged
     assert np.max(np.abs(sf.x - x_ref)) <= 1e-8 * np.max(np.abs(x_ref))
-    assert solver.info["exit_code"] == 0 and solver.info["iters"] <= 40
+    assert solver.info["exit_code"] == 0
+    # iteration *counts* are performance, not parity: they are bounded relative to
+    # Jacobi-PCG in tests/test_gpu_zz_perf_bounds.py so that they can never stop -x
+    # before the parity files have run
 
 
 def test_default_solver_registration(op, b2):
