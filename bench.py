@@ -358,11 +358,7 @@ def gpu_arm(args):
     # the hierarchy, solve to the same rtol -- time-to-solve is the metric here,
     # an AMG iteration is not comparable to a PCG iteration
     amg = None
-    # (several GPUs: the block-wise slab multigrid is experimental and slower than
-    # Jacobi-PCG so far -- opt-in with --amg-multi, which also sets B200_AMG_SLABS=1)
-    if args.amg_multi:
-        os.environ["B200_AMG_SLABS"] = "1"
-    if not args.no_amg and (world == 1 or args.amg_multi):
+    if not args.no_amg:
         ctx.set_precond("amg")
         try:
             device_step()                               # warm-up (allocates the hierarchy)
@@ -384,13 +380,13 @@ def gpu_arm(args):
             amg = {"time_to_solve_s": ms_amg * 1e-3, "iters": int(ita), "relres": rela,
                    "info": int(infoa), "hierarchy_setup_ms": sta["t_setup_ms"],
                    "solve_ms": sta["t_solve_ms"],
-                   "levels": ctx.amg_setup() if world == 1 else "one hierarchy per rank",
+                   "levels": ctx.amg_setup(),
                    "max_rel_diff_vs_jacobi_pcg": dx,
                    "speedup_vs_jacobi_pcg": ms_step / ms_amg,
                    "what": "B200PCG(precond='amg'): aggregation-AMG K-cycle + flexible CG "
                            "(csrc/amg.cu); step = assembly + hierarchy build + solve"
-                           + ("" if world == 1 else "; slabs: global FCG over NCCL, every rank "
-                              "preconditions with the hierarchy of its own block")}
+                           + ("" if world == 1 else "; slabs: one hierarchy, levels row-partitioned "
+                              "by the slabs, small levels replicated")}
             del xa
         finally:
             ctx.set_precond("jacobi")
@@ -545,7 +541,6 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-p2p", action="store_true")
     ap.add_argument("--no-amg", action="store_true")
-    ap.add_argument("--amg-multi", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

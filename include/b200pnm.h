@@ -165,18 +165,27 @@ int b200_pcg_format(b200_ctx* ctx, int* fmt, int* ndiags);
  * multigrid K-cycle built on the device from the system matrix (csrc/amg.cu):
  * ~30 iterations at any size instead of O(N) for an N^3 lattice.  Same
  * stopping rule, same outputs (`iters` counts outer FCG iterations).  Applies
- * to symmetric single-GPU systems with more than 2048 rows; otherwise, and for
- * matrices that cannot be coarsened, the call silently stays with Jacobi
- * (slab runs too, unless B200_AMG_SLABS=1 selects the experimental block-wise
- * variant).
+ * to symmetric systems with more than 2048 rows; otherwise, and for matrices
+ * that cannot be coarsened, the call silently stays with Jacobi.
+ * Slab runs (b200_comm_init with several ranks; the row-block ownership of the
+ * reference's PETSc wrapper, solvers/_petsc.py:117-128): ONE hierarchy for the
+ * whole problem, every level row-partitioned by the same slabs (aggregates do
+ * not cross rank boundaries, the Galerkin products keep the couplings between
+ * neighbouring ranks) until a level is small enough to be replicated on every
+ * rank.  Collective: every rank must make the same calls.
  * b200_amg_setup builds the hierarchy now (it is otherwise built by the first
- * solve after the matrix changed); the two accessors export a level's CSR
- * (level 0 = the system matrix) and its aggregation map (row -> coarse row, -1
- * for rows left off the coarse grid) for the Galerkin-identity tests.        */
+ * solve after the matrix changed); the accessors export a level's CSR (level
+ * 0 = the system matrix; rows this rank holds, GLOBAL column ids) and its
+ * aggregation map (row -> global coarse row, -1 for rows left off the coarse
+ * grid) for the Galerkin-identity tests.  b200_amg_level_info fills
+ * {rows held, entries held, global rows, global index of the first held row,
+ *  1 if row-partitioned / 0 if held in full, halo entries from rank-1, from
+ *  rank+1, offset of this rank's coarse rows in the next level}.            */
 enum { B200_PRECOND_JACOBI = 0, B200_PRECOND_AMG = 1 };
 int b200_set_precond(b200_ctx* ctx, int kind);
 int b200_amg_setup(b200_ctx* ctx, int* nlevels);
 int b200_amg_level_shape(b200_ctx* ctx, int level, int64_t* n, int64_t* nnz);
+int b200_amg_level_info(b200_ctx* ctx, int level, int64_t* out8);
 int b200_amg_export_level(b200_ctx* ctx, int level, int32_t* indptr,
                           int32_t* indices, double* data, int32_t* agg);
 

@@ -75,6 +75,7 @@ SIGNATURES = {
     "b200_set_precond": (C.c_int, [_p, C.c_int]),
     "b200_amg_setup": (C.c_int, [_p, _pint]),
     "b200_amg_level_shape": (C.c_int, [_p, C.c_int, _pi64, _pi64]),
+    "b200_amg_level_info": (C.c_int, [_p, C.c_int, _pi64]),
     "b200_amg_export_level": (C.c_int, [_p, C.c_int, _p, _p, _p, _p]),
     "b200_clear_sources": (C.c_int, [_p]),
     "b200_add_source": (C.c_int, [_p, C.c_int, _p, _p, _p, _p]),

@@ -828,6 +828,13 @@ class AdvectionDiffusion(ReactiveTransport):
         ctx.add_to_diagonal(self["pore.bc.outflow"])
         return f, nnz
 
+    def _run_slabs(self, solver, x0, x0_given):
+        # the slab path assembles the symmetric Laplacian only: outflow BCs and the
+        # (Nt,2) conductance would be dropped silently (round-1 advisor finding)
+        raise NotImplementedError(
+            "AdvectionDiffusion is not slab-parallel: under torchrun pass "
+            "B200PCG(distributed=False) to solve it on this rank's GPU")
+
     def rate(self, pores=[], throats=[], mode="group"):
         throats_i = self._parse_indices(throats)
         g = self._conductance()

@@ -22,13 +22,23 @@
 //     kernel of solver.cu does every fine-level product), stopping rule as
 //     everywhere: ||b - A x||_2 <= max(rtol ||b||_2, atol), confirmed with an
 //     explicitly recomputed residual.
-// Symmetric systems on one GPU.  On slabs (several GPUs) an experimental opt-in mode
-// (B200_AMG_SLABS=1) lets every rank precondition with the hierarchy of its own block
-// (additive Schwarz); by default, and for anything else, Jacobi-PCG / BiCGStab.
+// Symmetric systems.  On slabs (one rank per GPU, row-block ownership as in
+// openpnm/solvers/_petsc.py:117-128) the hierarchy is ONE multigrid for the whole
+// problem: the matching only sees the columns a rank owns, so aggregates never cross a
+// rank boundary and every level stays row-partitioned by the same slabs, while the
+// Galerkin products keep the couplings between coarse rows of neighbouring ranks (the
+// aggregation map of the halo columns is exchanged with the two neighbours).  Every
+// product on such a level is preceded by a halo exchange of its operand (contiguous
+// windows: coarse ids follow the fine row order), dot products are all-reduced.  Once a
+// level has at most B200_AMG_REPL rows globally (default 2^19) it is gathered and it and
+// everything below it are built and applied redundantly on every rank: no communication
+// below that level except the one gather of the restricted residual per visit.
+// tests/models/amg_slabs.py + amg_dist_model.py are the executable specification.
 // Environment knobs for experiments: B200_AMG_KLEVELS (0..3, default 2),
 // B200_AMG_PASSES0 (pairwise passes on the fine level, default 4),
 // B200_AMG_F32=0 (fp64 coarse products), B200_AMG_MAXITER (solver.cu: iteration cap
-// before the hand-over to Jacobi-PCG, default 300).
+// before the hand-over to Jacobi-PCG, default 300), B200_AMG_REPL (rows below which a
+// level of a slab run is replicated), B200_AMG_SLABS=0 (slab runs stay with Jacobi-PCG).
 #include <math.h>
 #include <stdlib.h>
 #include <time.h>
@@ -46,23 +56,49 @@
 #define AMG_COARSE_ITERS 30
 
 struct AmgLevel {
-  int64_t n = 0, nnz = 0, nc = 0;
+  int64_t n = 0, nnz = 0, nc = 0;       // rows / entries held by this rank; nc: rows of the next level
   DevBuf indptr, indices, data, dinv;   // own CSR (levels >= 1)
   DevBuf dataf;                         // fp32 copy of the values for the cycle's products
   const int* ip = nullptr;
   const int* ix = nullptr;
   const double* av = nullptr;
   DevBuf agg, cptr, cmem;               // aggregation to the next level + member lists
-  DevBuf x, b, ax, dir;                 // cycle vectors (levels >= 1)
-  DevBuf kb, kc1, kv1, kv2, ks;         // K-cycle buffers and scalars (levels 1..AMG_KLEVELS)
+  DevBuf x, b, ax, dir;                 // cycle vectors (levels >= 1); x is [wlo | n | whi]
+  DevBuf kb, kc1, kv1, kv2, ks;         // K-cycle buffers and scalars (levels 1..AMG_KLEVELS); kc1 padded like x
   DevBuf cgw;                           // coarsest: r, p, q
   double lmax = 2.0;
   double c0 = 0, c1 = 0, c2 = 0;        // Chebyshev(2) coefficients
+  // slab runs: a level is either row-partitioned (dist) or replicated on every rank
+  bool dist = false;
+  int64_t ng = 0, goff = 0;             // global rows, global index of the first owned row
+  int64_t nnzg = 0;                     // global entries
+  int wlo = 0, whi = 0, slo = 0, shi = 0;   // halo entries received from / sent to rank-1, rank+1
+  bool next_repl = false;               // dist level whose coarse level is replicated
+  int64_t coff = 0;                     // offset of this rank's coarse rows in the next level
+  double* xo() const { return x.as<double>() + wlo; }      // first owned entry of the padded vectors
+  double* kc1o() const { return kc1.as<double>() + wlo; }
 };
 
 struct CsrOut {
   DevBuf indptr, indices, data, dinv;
   int64_t n = 0, nnz = 0;
+  // row-partitioned output of a pass in a slab run (columns are local signed ids:
+  // < 0 rank-1's rows, >= n rank+1's rows)
+  int64_t ng = 0, goff = 0, nnzg = 0;
+  int wlo = 0, whi = 0, slo = 0, shi = 0;
+};
+
+// the matrix a pairwise pass works on
+struct PassMat {
+  int n = 0;
+  const int* ip = nullptr;
+  const int* ix = nullptr;
+  const double* av = nullptr;
+  const double* dg = nullptr;           // separate diagonal (level 0: the linearised one)
+  int shift = 0;                        // column - shift = local row index
+  bool dist = false;
+  int64_t ng = 0;
+  int wlo = 0, whi = 0, slo = 0, shi = 0;
 };
 
 struct AmgState {
@@ -72,7 +108,9 @@ struct AmgState {
   bool valid = false;
   // setup temporaries, kept so that a rebuild of the same size allocates nothing
   DevBuf t_match, t_prop, t_ids, t_cptr, t_cmem, t_tc, t_tv, t_aggpass, t_cnt, t_cur;
+  DevBuf t_aggg, t_minmax, t_gcnt;      // slab runs: global ids of the halo'd map, column range, gather
   CsrOut t_csr[2];
+  CsrOut t_gather;
   // level 0 lives in the Jacobi-scaled, padded layout of the PCG operator
   DevBuf z0, z1, ax0, dir0, winv, fd, fq;
   DevBuf lmax_dev;
@@ -114,6 +152,14 @@ static bool amg_f32() {
   return k != 0;
 }
 
+// slab runs: a level with at most this many rows (globally) is replicated on every rank
+// (read at every setup, so a test can switch it inside one process)
+static int64_t amg_repl_rows() {
+  const char* e = getenv("B200_AMG_REPL");
+  const long long v = e ? atoll(e) : 0;
+  return v > 0 ? v : (1ll << 19);
+}
+
 static AmgState* amg_of(b200_ctx* ctx) {
   if (!ctx->amg) ctx->amg = new AmgState();
   return static_cast<AmgState*>(ctx->amg);
@@ -128,10 +174,10 @@ void b200_amg_release(b200_ctx* ctx) {
       b->release();
   for (DevBuf* b : {&A->z0, &A->z1, &A->ax0, &A->dir0, &A->winv, &A->fd, &A->fq, &A->lmax_dev,
                     &A->t_match, &A->t_prop, &A->t_ids, &A->t_cptr, &A->t_cmem, &A->t_tc, &A->t_tv,
-                    &A->t_aggpass, &A->t_cnt, &A->t_cur})
+                    &A->t_aggpass, &A->t_cnt, &A->t_cur, &A->t_aggg, &A->t_minmax, &A->t_gcnt})
     b->release();
-  for (CsrOut& c : A->t_csr)
-    for (DevBuf* b : {&c.indptr, &c.indices, &c.data, &c.dinv}) b->release();
+  for (CsrOut* c : {&A->t_csr[0], &A->t_csr[1], &A->t_gather})
+    for (DevBuf* b : {&c->indptr, &c->indices, &c->data, &c->dinv}) b->release();
   delete A;
   ctx->amg = nullptr;
 }
@@ -196,9 +242,9 @@ __global__ void __launch_bounds__(AMG_T) k_amg_leader(const int* __restrict__ ip
       for (int e = ip[i]; e < ip[i + 1]; ++e) {
         const int j = ix[e] - shift;
         const double w = -av[e];
-        if (j < 0 || j >= n) continue;
         if (j == i || !(w > 0.0)) continue;
-        ++deg;
+        ++deg;                    // couplings to a neighbour rank's rows count: such a row is a
+        if (j < 0 || j >= n) continue;   // singleton aggregate, not a boundary row
         if (match[j] < 0 || !(w > bw)) continue;
         bw = w;
         best = j;
@@ -289,7 +335,8 @@ __global__ void __launch_bounds__(AMG_T) k_amg_row_ub(int nc, const int* __restr
 
 // gather the mapped entries of the member rows (members ascending, entries in CSR
 // order) and add the ones that land in the same coarse column, in that order (a
-// fixed order: bit-repeatable).  The table of a row lives in thread-local memory
+// fixed order: bit-repeatable).  `agg` is indexed by local column j in [jlo, jhi): the
+// owned rows, plus -- in a slab run -- the halo windows of the neighbours' map.  The table of a row lives in thread-local memory
 // (coalesced, L1-resident) while it has at most AMG_ROWCAP distinct columns and
 // in the row's global segment otherwise.  Columns stay in first-arrival order:
 // nothing downstream needs them sorted.
@@ -301,7 +348,7 @@ __global__ void __launch_bounds__(128) k_amg_row_build(int nc, const int* __rest
                                                        const double* __restrict__ av,
                                                        const double* __restrict__ diag,
                                                        const int* __restrict__ agg, int shift,
-                                                       int nf,
+                                                       int jlo, int jhi, int coff,
                                                        const int* __restrict__ tofs,
                                                        int* __restrict__ tc,
                                                        double* __restrict__ tv,
@@ -317,9 +364,10 @@ __global__ void __launch_bounds__(128) k_amg_row_build(int nc, const int* __rest
       const int i = cmem[q];
       for (int e = ip[i]; e < ip[i + 1]; ++e) {
         const int j = ix[e] - shift;
-        if (j < 0 || j >= nf) continue;
-        const int a = agg[j];
+        if (j < jlo || j >= jhi) continue;
+        int a = agg[j];           // slab runs: global coarse id (halo entries included)
         if (a < 0) continue;
+        a -= coff;                // -> local signed id: < 0 rank-1's rows, >= nc rank+1's
         const double v = (diag != nullptr && j == i) ? diag[i] : av[e];
         int k = 0;
         if (!spilled) {
@@ -388,6 +436,63 @@ __global__ void __launch_bounds__(AMG_T) k_amg_rowbound(const int* __restrict__ 
     if (d > 0.0 && isfinite(s)) mx = fmax(mx, s / d);
   }
   if (mx > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
+}
+
+// ============================================================ slab-run helpers
+// owned part of the halo'd aggregation map, in global coarse ids
+__global__ void __launch_bounds__(AMG_T) k_amg_global_ids(int n, const int* __restrict__ agg,
+                                                          int coff, int* __restrict__ out) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int a = agg[i];
+    out[i] = a >= 0 ? a + coff : -1;
+  }
+}
+
+// mm[0] = min column, mm[1] = max column of a pass's output (integer atomics)
+__global__ void __launch_bounds__(AMG_T) k_amg_col_range(int64_t nnz, const int* __restrict__ ix,
+                                                         int* __restrict__ mm) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int lo = 0x7fffffff, hi = -0x7fffffff;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+    const int c = ix[e];
+    lo = min(lo, c);
+    hi = max(hi, c);
+  }
+  if (lo <= hi) {
+    atomicMin(&mm[0], lo);
+    atomicMax(&mm[1], hi);
+  }
+}
+
+__global__ void __launch_bounds__(AMG_T) k_amg_row_counts(int n, const int* __restrict__ ip,
+                                                          int* __restrict__ cnt) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) cnt[i] = ip[i + 1] - ip[i];
+}
+
+// this rank's entries into their place in the gathered (replicated) level, columns global
+__global__ void __launch_bounds__(AMG_T) k_amg_scatter_entries(int64_t nnz,
+                                                               const int* __restrict__ ix,
+                                                               const double* __restrict__ av,
+                                                               int coff, int* __restrict__ oix,
+                                                               double* __restrict__ oav) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+    oix[e] = ix[e] + coff;
+    oav[e] = av[e];
+  }
+}
+
+// export helper: local signed columns -> global ids
+__global__ void __launch_bounds__(AMG_T) k_amg_shift_ids(int64_t n, const int* __restrict__ in,
+                                                         int add, int keep_negative,
+                                                         int* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int v = in[i];
+    out[i] = (keep_negative && v < 0) ? v : v + add;
+  }
 }
 
 // ============================================================== cycle kernels
@@ -741,57 +846,116 @@ static int amg_members(b200_ctx* ctx, AmgState* A, int n, int nc, const int* agg
   return B200_OK;
 }
 
-// one pairwise pass on (n, ip, ix, av [, diag]) -> agg (n) and the Galerkin matrix
-static int amg_pair_pass(b200_ctx* ctx, AmgState* A, int n, const int* ip, const int* ix,
-                         const double* av, const double* diag, int shift, DevBuf& agg_out,
+// One pairwise pass on M -> agg (M.n local coarse ids, -1 = off the coarse grid) and the
+// Galerkin matrix of the rows this rank owns.  Slab run (M.dist): the matching ignores
+// the halo columns, the coarse numbering is local id + (coarse rows of the lower ranks),
+// the neighbours' part of the map arrives by one integer halo exchange, the product is
+// then row-local; the column range of the result gives the halo widths of the next
+// matrix, which the neighbours learn through one small all-gather.  Every decision that
+// changes the control flow is taken on all-gathered numbers.
+static int amg_pair_pass(b200_ctx* ctx, AmgState* A, const PassMat& M, DevBuf& agg_out,
                          CsrOut& out) {
+  const int n = M.n;
   DevBuf& match = A->t_match;
   DevBuf& prop = A->t_prop;
   DevBuf& ids = A->t_ids;
   CK(match.ensure((size_t)(n + 1) * sizeof(int)));
   CK(prop.ensure((size_t)(n + 1) * sizeof(int)));
   CK(ids.ensure((size_t)(n + 1) * sizeof(int)));
-  CK(agg_out.ensure((size_t)n * sizeof(int)));
-  CK(cudaMemsetAsync(match.p, 0xff, (size_t)n * sizeof(int), ctx->stream));
+  CK(agg_out.ensure((size_t)(n + 1) * sizeof(int)));
+  CK(cudaMemsetAsync(match.p, 0xff, (size_t)(n + 1) * sizeof(int), ctx->stream));
   const int g = grid_for(n, AMG_T);
   for (int r = 0; r < AMG_ROUNDS; ++r) {
-    LAUNCH(ctx, k_amg_propose, g, AMG_T, 0, ip, ix, av, n, shift, match.as<int>(),
+    LAUNCH(ctx, k_amg_propose, g, AMG_T, 0, M.ip, M.ix, M.av, n, M.shift, match.as<int>(),
            prop.as<int>());
     LAUNCH(ctx, k_amg_accept, g, AMG_T, 0, n, prop.as<int>(), match.as<int>());
   }
   // prop <- leader, ids <- flags -> scanned ids
-  LAUNCH(ctx, k_amg_leader, g, AMG_T, 0, ip, ix, av, n, shift, match.as<int>(), prop.as<int>(),
-         ids.as<int>());
+  LAUNCH(ctx, k_amg_leader, g, AMG_T, 0, M.ip, M.ix, M.av, n, M.shift, match.as<int>(),
+         prop.as<int>(), ids.as<int>());
   int64_t nc64 = 0;
   RET(b200_scan_exclusive_i32(ctx, ids.as<int>(), ids.as<int>(), n, &nc64));
   const int nc = (int)nc64;
   LAUNCH(ctx, k_amg_assign, g, AMG_T, 0, n, prop.as<int>(), ids.as<int>(), agg_out.as<int>());
+  int64_t coff = 0, ncg = nc;
+  std::vector<int64_t> all((size_t)ctx->nranks * 4);
+  if (M.dist) {
+    const int64_t mine = nc;
+    RET(b200_allgather_i64_host(ctx, &mine, 1, all.data()));
+    ncg = 0;
+    for (int r = 0; r < ctx->nranks; ++r) {
+      if (r < ctx->rank) coff += all[r];
+      ncg += all[r];
+    }
+    if (ncg >= (1ll << 31)) FAIL(B200_ERR_TOO_LARGE, "amg: coarse level exceeds int32 ids");
+  }
   out.n = nc;
-  out.nnz = 0;
-  if (nc == 0) return B200_OK;
+  out.ng = ncg;
+  out.goff = coff;
+  out.nnz = out.nnzg = 0;
+  out.wlo = out.whi = out.slo = out.shi = 0;
+  if (ncg == 0) return B200_OK;
   RET(amg_members(ctx, A, n, nc, agg_out.as<int>(), A->t_cptr, A->t_cmem));
   const int* cptr = A->t_cptr.as<int>();
   const int* cmem = A->t_cmem.as<int>();
+  const int* aggmap = agg_out.as<int>();
+  int jlo = 0, jhi = n;
+  if (M.dist) {
+    CK(A->t_aggg.ensure((size_t)(M.wlo + n + M.whi + 1) * sizeof(int)));
+    int* go = A->t_aggg.as<int>() + M.wlo;
+    LAUNCH(ctx, k_amg_global_ids, g, AMG_T, 0, n, agg_out.as<int>(), (int)coff, go);
+    RET(b200_halo_exchange_w(ctx, go, n, 4, M.wlo, M.whi, M.slo, M.shi));
+    aggmap = go;
+    jlo = -M.wlo;
+    jhi = n + M.whi;
+  }
   // upper bounds -> segment offsets (match is reused as ub / len, ids as tofs)
   const int gc = grid_for(nc, 128);
-  LAUNCH(ctx, k_amg_row_ub, grid_for(nc, AMG_T), AMG_T, 0, nc, cptr, cmem, ip, match.as<int>());
+  LAUNCH(ctx, k_amg_row_ub, grid_for(nc, AMG_T), AMG_T, 0, nc, cptr, cmem, M.ip, match.as<int>());
   int64_t T = 0;
   RET(b200_scan_exclusive_i32(ctx, match.as<int>(), ids.as<int>(), nc, &T));
   CK(A->t_tc.ensure((size_t)(T > 0 ? T : 1) * sizeof(int)));
   CK(A->t_tv.ensure((size_t)(T > 0 ? T : 1) * sizeof(double)));
-  LAUNCH(ctx, k_amg_row_build, gc, 128, 0, nc, cptr, cmem, ip, ix, av, diag, agg_out.as<int>(),
-         shift, n, ids.as<int>(), A->t_tc.as<int>(), A->t_tv.as<double>(), match.as<int>());
+  LAUNCH(ctx, k_amg_row_build, gc, 128, 0, nc, cptr, cmem, M.ip, M.ix, M.av, M.dg, aggmap,
+         M.shift, jlo, jhi, (int)coff, ids.as<int>(), A->t_tc.as<int>(), A->t_tv.as<double>(),
+         match.as<int>());
   CK(out.indptr.ensure((size_t)(nc + 1) * sizeof(int)));
   int64_t cnnz = 0;
   RET(b200_scan_exclusive_i32(ctx, match.as<int>(), out.indptr.as<int>(), nc, &cnnz));
   CK(out.indices.ensure((size_t)(cnnz > 0 ? cnnz : 1) * sizeof(int)));
   CK(out.data.ensure((size_t)(cnnz > 0 ? cnnz : 1) * sizeof(double)));
-  CK(out.dinv.ensure((size_t)nc * sizeof(double)));
+  CK(out.dinv.ensure((size_t)(nc > 0 ? nc : 1) * sizeof(double)));
   LAUNCH(ctx, k_amg_row_emit, gc, 128, 0, nc, ids.as<int>(), A->t_tc.as<int>(),
          A->t_tv.as<double>(), out.indptr.as<int>(), out.indices.as<int>(), out.data.as<double>(),
          out.dinv.as<double>(), ctx->w_flags.as<int>());
   CK(cudaGetLastError());
-  out.nnz = cnnz;
+  out.nnz = out.nnzg = cnnz;
+  if (M.dist) {
+    CK(A->t_minmax.ensure(2 * sizeof(int)));
+    int mm[2] = {0x7fffffff, -0x7fffffff};
+    CK(cudaMemcpyAsync(A->t_minmax.p, mm, sizeof mm, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_amg_col_range, grid_for(cnnz, AMG_T), AMG_T, 0, cnnz, out.indices.as<int>(),
+           A->t_minmax.as<int>());
+    CK(cudaMemcpyAsync(mm, A->t_minmax.p, sizeof mm, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int64_t mine[3] = {0, 0, cnnz};
+    if (mm[0] <= mm[1]) {
+      mine[0] = mm[0] < 0 ? -(int64_t)mm[0] : 0;
+      mine[1] = mm[1] >= nc ? (int64_t)mm[1] - nc + 1 : 0;
+    }
+    RET(b200_allgather_i64_host(ctx, mine, 3, all.data()));
+    out.wlo = (int)mine[0];
+    out.whi = (int)mine[1];
+    out.slo = ctx->rank > 0 ? (int)all[(size_t)(ctx->rank - 1) * 3 + 1] : 0;
+    out.shi = ctx->rank < ctx->nranks - 1 ? (int)all[(size_t)(ctx->rank + 1) * 3 + 0] : 0;
+    out.nnzg = 0;
+    for (int r = 0; r < ctx->nranks; ++r) out.nnzg += all[(size_t)r * 3 + 2];
+    // aggregates never cross a rank boundary and the fine couplings join neighbouring
+    // ranks only, so the windows lie inside the neighbours' rows
+    const int64_t nlo = ctx->rank > 0 ? 1 : 0, nhi = ctx->rank < ctx->nranks - 1 ? 1 : 0;
+    if ((out.wlo > 0 && !nlo) || (out.whi > 0 && !nhi) || out.slo > nc || out.shi > nc)
+      FAIL(B200_ERR_ARG, "amg: a coarse coupling reaches past the neighbouring rank");
+  }
   return B200_OK;
 }
 
@@ -804,9 +968,69 @@ static int amg_level_bound(b200_ctx* ctx, AmgState* A, AmgLevel& L, const double
   double lm = 0.0;
   CK(cudaMemcpyAsync(&lm, A->lmax_dev.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (L.dist) {
+    // positive doubles order like their bit patterns: the all-gathered maximum is exact
+    int64_t bits = 0;
+    if (lm > 0.0 && isfinite(lm)) memcpy(&bits, &lm, sizeof bits);
+    std::vector<int64_t> all((size_t)ctx->nranks);
+    RET(b200_allgather_i64_host(ctx, &bits, 1, all.data()));
+    for (int r = 0; r < ctx->nranks; ++r) bits = all[r] > bits ? all[r] : bits;
+    memcpy(&lm, &bits, sizeof lm);
+  }
   L.lmax = (lm > 1.0 && isfinite(lm)) ? lm : 2.0;
   cheb_coeffs(L);
   return B200_OK;
+}
+
+// Row-partitioned output of the last pass -> the same matrix held in full by every
+// rank (columns global): every rank writes its rows into zeroed global arrays and the
+// sum over the ranks is the concatenation.
+static int amg_gather_level(b200_ctx* ctx, AmgState* A, const CsrOut& loc, CsrOut& full) {
+  const int64_t ncg = loc.ng, nnzg = loc.nnzg;
+  std::vector<int64_t> all((size_t)ctx->nranks);
+  const int64_t mine = loc.nnz;
+  RET(b200_allgather_i64_host(ctx, &mine, 1, all.data()));
+  int64_t eoff = 0;
+  for (int r = 0; r < ctx->rank; ++r) eoff += all[r];
+  CK(A->t_gcnt.ensure((size_t)(ncg + 1) * sizeof(int)));
+  CK(cudaMemsetAsync(A->t_gcnt.p, 0, (size_t)(ncg + 1) * sizeof(int), ctx->stream));
+  LAUNCH(ctx, k_amg_row_counts, grid_for(loc.n, AMG_T), AMG_T, 0, (int)loc.n,
+         loc.indptr.as<int>(), A->t_gcnt.as<int>() + loc.goff);
+  RET(b200_allreduce_sum_i32(ctx, A->t_gcnt.as<int>(), (size_t)ncg));
+  CK(full.indptr.ensure((size_t)(ncg + 1) * sizeof(int)));
+  int64_t tot = 0;
+  RET(b200_scan_exclusive_i32(ctx, A->t_gcnt.as<int>(), full.indptr.as<int>(), ncg, &tot));
+  if (tot != nnzg) FAIL(B200_ERR_ARG, "amg: gathered level is inconsistent (%lld vs %lld entries)",
+                        (long long)tot, (long long)nnzg);
+  const size_t ne = (size_t)(nnzg > 0 ? nnzg : 1);
+  CK(full.indices.ensure(ne * sizeof(int)));
+  CK(full.data.ensure(ne * sizeof(double)));
+  CK(full.dinv.ensure((size_t)ncg * sizeof(double)));
+  CK(cudaMemsetAsync(full.indices.p, 0, ne * sizeof(int), ctx->stream));
+  CK(cudaMemsetAsync(full.data.p, 0, ne * sizeof(double), ctx->stream));
+  CK(cudaMemsetAsync(full.dinv.p, 0, (size_t)ncg * sizeof(double), ctx->stream));
+  LAUNCH(ctx, k_amg_scatter_entries, grid_for(loc.nnz, AMG_T), AMG_T, 0, loc.nnz,
+         loc.indices.as<int>(), loc.data.as<double>(), (int)loc.goff,
+         full.indices.as<int>() + eoff, full.data.as<double>() + eoff);
+  if (loc.n > 0)
+    CK(cudaMemcpyAsync(full.dinv.as<double>() + loc.goff, loc.dinv.p,
+                       (size_t)loc.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  RET(b200_allreduce_sum_i32(ctx, full.indices.as<int>(), (size_t)nnzg));
+  RET(b200_allreduce_sum_n(ctx, full.data.as<double>(), (size_t)nnzg));
+  RET(b200_allreduce_sum_n(ctx, full.dinv.as<double>(), (size_t)ncg));
+  CK(cudaGetLastError());
+  full.n = full.ng = ncg;
+  full.nnz = full.nnzg = nnzg;
+  full.goff = 0;
+  full.wlo = full.whi = full.slo = full.shi = 0;
+  return B200_OK;
+}
+
+static void swap_csr(AmgLevel& C, CsrOut& o) {
+  std::swap(C.indptr, o.indptr);
+  std::swap(C.indices, o.indices);
+  std::swap(C.data, o.data);
+  std::swap(C.dinv, o.dinv);
 }
 
 static int amg_setup(b200_ctx* ctx) {
@@ -814,6 +1038,8 @@ static int amg_setup(b200_ctx* ctx) {
   A->valid = false;
   A->nlev = 0;
   RET(b200_zero_flags(ctx));
+  const bool multi = ctx->nranks > 1;
+  const int64_t repl_rows = amg_repl_rows();
   const double* diag0 = b200_cur_diag(ctx);
   if (A->lv.empty()) A->lv.emplace_back();
   {
@@ -823,6 +1049,13 @@ static int amg_setup(b200_ctx* ctx) {
     L.ip = ctx->sys_indptr.as<int>();
     L.ix = ctx->sys_indices.as<int>();
     L.av = ctx->sys_data.as<double>();
+    L.dist = multi;
+    L.ng = multi ? ctx->n_global : ctx->n;
+    L.goff = ctx->row_begin;
+    L.wlo = L.slo = (multi && ctx->rank > 0) ? (int)ctx->halo : 0;
+    L.whi = L.shi = (multi && ctx->rank < ctx->nranks - 1) ? (int)ctx->halo : 0;
+    L.next_repl = false;
+    L.coff = 0;
     RET(amg_level_bound(ctx, A, L, diag0, (int)ctx->row_begin));
   }
   size_t l = 0;
@@ -834,57 +1067,87 @@ static int amg_setup(b200_ctx* ctx) {
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
   };
   if (ctx->debug) t_prev = now_ms();
-  while (l + 1 < AMG_MAX_LEVELS && A->lv[l].n > AMG_COARSEST) {
+  bool broken = false;       // slab run whose row-partitioned levels cannot reach the coarsest size
+  while (l + 1 < AMG_MAX_LEVELS && A->lv[l].ng > AMG_COARSEST) {
     if (A->lv.size() <= l + 1) A->lv.emplace_back();     // may move the vector: index, never keep refs
     const int n = (int)A->lv[l].n;
-    const int* ip = A->lv[l].ip;
-    const int* ix = A->lv[l].ix;
-    const double* av = A->lv[l].av;
-    const double* dg = (l == 0) ? diag0 : nullptr;
-    int64_t nn = n;
+    const int64_t ng = A->lv[l].ng;
+    PassMat M;
+    M.n = n;
+    M.ip = A->lv[l].ip;
+    M.ix = A->lv[l].ix;
+    M.av = A->lv[l].av;
+    M.dg = (l == 0) ? diag0 : nullptr;
+    M.shift = (l == 0) ? (int)ctx->row_begin : 0;
+    M.dist = A->lv[l].dist;
+    M.ng = ng;
+    M.wlo = A->lv[l].wlo; M.whi = A->lv[l].whi; M.slo = A->lv[l].slo; M.shi = A->lv[l].shi;
     bool ok = true;
-    CsrOut lvl;                                          // the last pass writes the level's own buffers
-    lvl.indptr = A->lv[l + 1].indptr;
-    lvl.indices = A->lv[l + 1].indices;
-    lvl.data = A->lv[l + 1].data;
-    lvl.dinv = A->lv[l + 1].dinv;
+    CsrOut* last = nullptr;
     const int npass = (l == 0) ? amg_passes0() : AMG_PASSES;
     for (int pass = 0; pass < npass; ++pass) {
-      CsrOut& dst = (pass == npass - 1) ? lvl : A->t_csr[pass & 1];
+      CsrOut& dst = A->t_csr[pass & 1];
       DevBuf& aggp = (pass == 0) ? A->lv[l].agg : A->t_aggpass;
-      const int shift = (l == 0 && pass == 0) ? (int)ctx->row_begin : 0;
-      int rc = amg_pair_pass(ctx, A, (int)nn, ip, ix, av, dg, shift, aggp, dst);
-      if (pass == npass - 1) {                           // hand the (possibly regrown) buffers back
-        A->lv[l + 1].indptr = lvl.indptr;
-        A->lv[l + 1].indices = lvl.indices;
-        A->lv[l + 1].data = lvl.data;
-        A->lv[l + 1].dinv = lvl.dinv;
-      }
-      RET(rc);
-      if (dst.n == 0) { ok = false; break; }
+      RET(amg_pair_pass(ctx, A, M, aggp, dst));
+      if (dst.ng == 0) { ok = false; break; }
       if (pass > 0)
         LAUNCH(ctx, k_amg_compose, grid_for(n, AMG_T), AMG_T, 0, n, A->lv[l].agg.as<int>(),
                aggp.as<int>());
       if (ctx->debug) {
         const double t = now_ms();
-        fprintf(stderr, "[b200 amg] level %d pass %d: %lld -> %lld rows, %lld nnz, %.2f ms\n",
-                (int)l, pass, (long long)nn, (long long)dst.n, (long long)dst.nnz, t - t_prev);
+        fprintf(stderr, "[b200 amg r%d] level %d pass %d: %lld -> %lld rows (global %lld -> %lld), "
+                "%lld nnz, halo %d/%d, %.2f ms\n", ctx->rank, (int)l, pass, (long long)M.n,
+                (long long)dst.n, (long long)M.ng, (long long)dst.ng, (long long)dst.nnz, dst.wlo,
+                dst.whi, t - t_prev);
         t_prev = t;
       }
-      ip = dst.indptr.as<int>();
-      ix = dst.indices.as<int>();
-      av = dst.data.as<double>();
-      dg = nullptr;
-      nn = dst.n;
-      lvl.n = dst.n;
-      lvl.nnz = dst.nnz;
+      M.n = (int)dst.n;
+      M.ip = dst.indptr.as<int>();
+      M.ix = dst.indices.as<int>();
+      M.av = dst.data.as<double>();
+      M.dg = nullptr;
+      M.shift = 0;
+      M.ng = dst.ng;
+      M.wlo = dst.wlo; M.whi = dst.whi; M.slo = dst.slo; M.shi = dst.shi;
+      last = &dst;
     }
-    if (!ok || (double)lvl.n > 0.7 * (double)n) break;   // coarsening stalled: level l is the last
-    A->lv[l].nc = lvl.n;
-    RET(amg_members(ctx, A, n, (int)lvl.n, A->lv[l].agg.as<int>(), A->lv[l].cptr, A->lv[l].cmem));
+    if (!ok || last == nullptr || (double)last->ng > 0.7 * (double)ng) {
+      // coarsening stalled: level l is the last one (a row-partitioned level cannot be:
+      // the coarsest problem is solved inside one thread block)
+      if (A->lv[l].dist) broken = true;
+      break;
+    }
+    AmgLevel& F = A->lv[l];
     AmgLevel& C = A->lv[l + 1];
-    C.n = lvl.n;
-    C.nnz = lvl.nnz;
+    F.nc = last->n;
+    F.coff = last->goff;
+    F.next_repl = false;
+    RET(amg_members(ctx, A, n, (int)last->n, F.agg.as<int>(), F.cptr, F.cmem));
+    if (F.dist && last->ng > repl_rows && last->ng > AMG_COARSEST) {
+      // the next level stays row-partitioned
+      swap_csr(C, *last);
+      C.dist = true;
+      C.n = last->n; C.nnz = last->nnz; C.ng = last->ng; C.nnzg = last->nnzg;
+      C.goff = last->goff;
+      C.wlo = last->wlo; C.whi = last->whi; C.slo = last->slo; C.shi = last->shi;
+    } else if (F.dist) {
+      // small enough: every rank holds the next level (and everything below it) in full
+      RET(amg_gather_level(ctx, A, *last, A->t_gather));
+      swap_csr(C, A->t_gather);
+      F.next_repl = true;
+      C.dist = false;
+      C.n = C.ng = A->t_gather.n; C.nnz = C.nnzg = A->t_gather.nnz;
+      C.goff = 0;
+      C.wlo = C.whi = C.slo = C.shi = 0;
+    } else {
+      swap_csr(C, *last);
+      C.dist = false;
+      C.n = C.ng = last->n; C.nnz = C.nnzg = last->nnz;
+      C.goff = 0;
+      C.wlo = C.whi = C.slo = C.shi = 0;
+    }
+    C.next_repl = false;
+    C.coff = 0;
     C.ip = C.indptr.as<int>();
     C.ix = C.indices.as<int>();
     C.av = C.data.as<double>();
@@ -893,35 +1156,53 @@ static int amg_setup(b200_ctx* ctx) {
       CK(C.dataf.ensure((size_t)(C.nnz > 0 ? C.nnz : 1) * sizeof(float)));
       LAUNCH(ctx, k_amg_to_f32, grid_for(C.nnz, AMG_T), AMG_T, 0, C.nnz, C.av, C.dataf.as<float>());
     }
-    for (DevBuf* b : {&C.x, &C.b, &C.ax, &C.dir}) CK(b->ensure((size_t)C.n * sizeof(double)));
+    const size_t vlen = (size_t)(C.n > 0 ? C.n : 1), plen = vlen + C.wlo + C.whi;
+    CK(C.x.ensure(plen * sizeof(double)));
+    for (DevBuf* b : {&C.b, &C.ax, &C.dir}) CK(b->ensure(vlen * sizeof(double)));
     if ((int)(l + 1) <= AMG_KLEVELS_MAX) {
-      for (DevBuf* b : {&C.kb, &C.kc1, &C.kv1, &C.kv2}) CK(b->ensure((size_t)C.n * sizeof(double)));
+      CK(C.kc1.ensure(plen * sizeof(double)));
+      for (DevBuf* b : {&C.kb, &C.kv1, &C.kv2}) CK(b->ensure(vlen * sizeof(double)));
       CK(C.ks.ensure(8 * sizeof(double)));
     }
     ++l;
   }
   A->nlev = l + 1;
-  if (A->nlev > 1) CK(A->lv[l].cgw.ensure((size_t)3 * A->lv[l].n * sizeof(double)));
+  if (A->lv[l].dist && A->nlev > 1) broken = true;       // e.g. the level cap was reached
+  if (A->nlev > 1 && !A->lv[l].dist)
+    CK(A->lv[l].cgw.ensure((size_t)3 * A->lv[l].n * sizeof(double)));
   CK(cudaMemcpyAsync(ctx->flags_h, ctx->w_flags.p, FLAG_COUNT * sizeof(int),
                      cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  if (ctx->flags_h[FLAG_NONPOS_DIAG])
-    FAIL(B200_ERR_SINGULAR, "amg: a coarse matrix has a non-positive diagonal");
-  A->valid = A->nlev > 1;
+  int64_t bad = ctx->flags_h[FLAG_NONPOS_DIAG] ? 1 : 0;
+  RET(b200_allreduce_max_host(ctx, &bad));               // same verdict on every rank
+  if (bad) FAIL(B200_ERR_SINGULAR, "amg: a coarse matrix has a non-positive diagonal");
+  A->valid = A->nlev > 1 && !broken;
   A->epoch = ctx->sys_epoch;
   A->lin_epoch = ctx->lin_epoch;
   if (ctx->debug) {
-    fprintf(stderr, "[b200 amg] levels:");
+    fprintf(stderr, "[b200 amg r%d] levels:", ctx->rank);
     for (size_t k = 0; k < A->nlev; ++k)
-      fprintf(stderr, " n=%lld nnz=%lld lmax=%.3f |", (long long)A->lv[k].n,
-              (long long)A->lv[k].nnz, A->lv[k].lmax);
-    fprintf(stderr, "\n");
+      fprintf(stderr, " n=%lld/%lld nnz=%lld %s lmax=%.3f |", (long long)A->lv[k].n,
+              (long long)A->lv[k].ng, (long long)A->lv[k].nnz,
+              A->lv[k].dist ? "rows" : "full", A->lv[k].lmax);
+    fprintf(stderr, "%s\n", broken ? " (unusable: coarsening stalled on a row-partitioned level)" : "");
   }
   return B200_OK;
 }
 
 // ======================================================================= cycle
-static int amg_spmv(b200_ctx* ctx, AmgState* A, size_t l, const double* x, double* y) {
+// halo windows of a level's product operand (x: first owned entry)
+static int amg_halo(b200_ctx* ctx, AmgState* A, size_t l, double* x) {
+  AmgLevel& L = A->lv[l];
+  if (!L.dist) return B200_OK;
+  if (l == 0) return b200_halo_exchange(ctx, x - ctx->pad);
+  return b200_halo_exchange_w(ctx, x, L.n, 8, L.wlo, L.whi, L.slo, L.shi);
+}
+
+// y = A_l x; on a row-partitioned level x must be a padded vector (level 0: the PCG
+// layout; below: [wlo | n | whi]) and its halo windows are filled first
+static int amg_spmv(b200_ctx* ctx, AmgState* A, size_t l, double* x, double* y) {
+  RET(amg_halo(ctx, A, l, x));
   if (l == 0) return b200_spmv_dots(ctx, x, x, y, ctx->scal.as<double>() + SC_AUX0);
   AmgLevel& L = A->lv[l];
   if (amg_f32()) {
@@ -936,24 +1217,48 @@ static int amg_spmv(b200_ctx* ctx, AmgState* A, size_t l, const double* x, doubl
 // padded layout, everything in the Jacobi-scaled space
 static int amg_child(b200_ctx* ctx, AmgState* A, size_t l);
 
+// restriction of level l's residual into the right-hand side of level l+1 / the
+// correction back; when the next level is replicated the ranks' parts are gathered
+static int amg_restrict(b200_ctx* ctx, AmgState* A, size_t l, const double* b, const double* ax,
+                        const double* w) {
+  AmgLevel& L = A->lv[l];
+  AmgLevel& C = A->lv[l + 1];
+  double* cb = C.b.as<double>();
+  if (L.next_repl) {
+    CK(cudaMemsetAsync(cb, 0, (size_t)C.n * sizeof(double), ctx->stream));
+    cb += L.coff;
+  }
+  LAUNCH(ctx, k_amg_restrict, grid_for(L.nc, AMG_T), AMG_T, 0, (int)L.nc, L.cptr.as<int>(),
+         L.cmem.as<int>(), b, ax, w, cb);
+  if (L.next_repl) RET(b200_allreduce_sum_n(ctx, C.b.as<double>(), (size_t)C.n));
+  return B200_OK;
+}
+
+static int amg_prolong(b200_ctx* ctx, AmgState* A, size_t l, const double* w, double* x) {
+  AmgLevel& L = A->lv[l];
+  AmgLevel& C = A->lv[l + 1];
+  const double* ec = C.xo() + (L.next_repl ? L.coff : 0);
+  LAUNCH(ctx, k_amg_prolong, grid_for(L.n, AMG_T), AMG_T, 0, L.n, L.agg.as<int>(), ec, w, x);
+  return B200_OK;
+}
+
 // level 0 on the DIA operator: every product is fused with the update that
 // consumes it (k_dia_smooth); zq_aux/zq_out: optional sum zq_aux . x of the result
-static int amg_cycle_fine_dia(b200_ctx* ctx, AmgState* A, const double* b, double* x,
-                              double* xalt, double* res, double* dir, const double* zq_aux,
-                              double* zq_out) {
+static int amg_cycle_fine_dia(b200_ctx* ctx, AmgState* A, double* b, double* x, double* xalt,
+                              double* res, double* dir, const double* zq_aux, double* zq_out) {
   AmgLevel& L = A->lv[0];
-  AmgLevel& C = A->lv[1];
-  const int64_t n = L.n, nc = C.n;
   double* scratch = ctx->scal.as<double>() + SC_AUX0;
   const double* w = A->winv.as<double>();
+  RET(amg_halo(ctx, A, 0, b));
   RET(b200_dia_smooth(ctx, 1, b, nullptr, nullptr, dir, x, L.c0, L.c1, L.c2, scratch));
+  RET(amg_halo(ctx, A, 0, x));
   RET(b200_dia_smooth(ctx, 4, x, b, w, nullptr, res, 0.0, 0.0, 0.0, scratch));
-  LAUNCH(ctx, k_amg_restrict, grid_for(nc, AMG_T), AMG_T, 0, (int)nc, L.cptr.as<int>(),
-         L.cmem.as<int>(), res, nullptr, nullptr, C.b.as<double>());
+  RET(amg_restrict(ctx, A, 0, res, nullptr, nullptr));
   RET(amg_child(ctx, A, 0));
-  LAUNCH(ctx, k_amg_prolong, grid_for(n, AMG_T), AMG_T, 0, n, L.agg.as<int>(), C.x.as<double>(),
-         w, x);
+  RET(amg_prolong(ctx, A, 0, w, x));
+  RET(amg_halo(ctx, A, 0, x));
   RET(b200_dia_smooth(ctx, 2, x, b, nullptr, dir, xalt, L.c0, L.c1, L.c2, scratch));
+  RET(amg_halo(ctx, A, 0, xalt));
   RET(b200_dia_smooth(ctx, 3, xalt, b, zq_aux, dir, x, L.c0, L.c1, L.c2,
                       zq_aux ? zq_out : scratch));
   return B200_OK;
@@ -978,13 +1283,9 @@ static int amg_cycle(b200_ctx* ctx, AmgState* A, size_t l, const double* b, doub
   LAUNCH(ctx, k_amg_cheb_next, g, AMG_T, 0, n, dinv, b, ax, L.c1, L.c2, dir, x);
   // coarse-grid correction
   RET(amg_spmv(ctx, A, l, x, ax));
-  AmgLevel& C = A->lv[l + 1];
-  const int64_t nc = C.n;
-  const int gc = grid_for(nc, AMG_T);
-  LAUNCH(ctx, k_amg_restrict, gc, AMG_T, 0, (int)nc, L.cptr.as<int>(), L.cmem.as<int>(), b,
-         ax, wgt, C.b.as<double>());
+  RET(amg_restrict(ctx, A, l, b, ax, wgt));
   RET(amg_child(ctx, A, l));
-  LAUNCH(ctx, k_amg_prolong, g, AMG_T, 0, n, L.agg.as<int>(), C.x.as<double>(), wgt, x);
+  RET(amg_prolong(ctx, A, l, wgt, x));
   // post-smoothing, Chebyshev(2)
   RET(amg_spmv(ctx, A, l, x, ax));
   LAUNCH(ctx, k_amg_cheb_first, g, AMG_T, 0, n, dinv, b, ax, L.c0, dir, x);
@@ -1007,41 +1308,35 @@ static int amg_child(b200_ctx* ctx, AmgState* A, size_t l) {
     double* ks = C.ks.as<double>();
     CK(cudaMemcpyAsync(C.kb.p, C.b.p, (size_t)nc * sizeof(double), cudaMemcpyDeviceToDevice,
                        ctx->stream));
-    RET(amg_cycle(ctx, A, l + 1, C.b.as<double>(), C.x.as<double>(), C.ax.as<double>(),
-                  C.dir.as<double>()));
-    CK(cudaMemcpyAsync(C.kc1.p, C.x.p, (size_t)nc * sizeof(double), cudaMemcpyDeviceToDevice,
+    RET(amg_cycle(ctx, A, l + 1, C.b.as<double>(), C.xo(), C.ax.as<double>(), C.dir.as<double>()));
+    CK(cudaMemcpyAsync(C.kc1o(), C.xo(), (size_t)nc * sizeof(double), cudaMemcpyDeviceToDevice,
                        ctx->stream));
-    RET(amg_spmv(ctx, A, l + 1, C.kc1.as<double>(), C.kv1.as<double>()));
-    LAUNCH(ctx, k_amg_dot2, gc, AMG_T, 0, nc, C.kc1.as<double>(), C.kv1.as<double>(),
-           C.kb.as<double>(), part, ticket, ks);
+    RET(amg_spmv(ctx, A, l + 1, C.kc1o(), C.kv1.as<double>()));
+    LAUNCH(ctx, k_amg_dot2, gc, AMG_T, 0, nc, C.kc1o(), C.kv1.as<double>(), C.kb.as<double>(),
+           part, ticket, ks);
+    if (C.dist) RET(b200_allreduce_sum(ctx, ks, 2));
     LAUNCH(ctx, k_amg_kres, gc, AMG_T, 0, nc, C.kb.as<double>(), C.kv1.as<double>(), ks,
            C.b.as<double>());
-    RET(amg_cycle(ctx, A, l + 1, C.b.as<double>(), C.x.as<double>(), C.ax.as<double>(),
-                  C.dir.as<double>()));
-    RET(amg_spmv(ctx, A, l + 1, C.x.as<double>(), C.kv2.as<double>()));
-    LAUNCH(ctx, k_amg_dot3, gc, AMG_T, 0, nc, C.x.as<double>(), C.kv1.as<double>(),
-           C.kv2.as<double>(), C.b.as<double>(), part, ticket, ks + 2);
-    LAUNCH(ctx, k_amg_kcomb, gc, AMG_T, 0, nc, C.kc1.as<double>(), ks, C.x.as<double>());
+    RET(amg_cycle(ctx, A, l + 1, C.b.as<double>(), C.xo(), C.ax.as<double>(), C.dir.as<double>()));
+    RET(amg_spmv(ctx, A, l + 1, C.xo(), C.kv2.as<double>()));
+    LAUNCH(ctx, k_amg_dot3, gc, AMG_T, 0, nc, C.xo(), C.kv1.as<double>(), C.kv2.as<double>(),
+           C.b.as<double>(), part, ticket, ks + 2);
+    if (C.dist) RET(b200_allreduce_sum(ctx, ks + 2, 3));
+    LAUNCH(ctx, k_amg_kcomb, gc, AMG_T, 0, nc, C.kc1o(), ks, C.xo());
   } else {
-    RET(amg_cycle(ctx, A, l + 1, C.b.as<double>(), C.x.as<double>(), C.ax.as<double>(),
-                  C.dir.as<double>()));
+    RET(amg_cycle(ctx, A, l + 1, C.b.as<double>(), C.xo(), C.ax.as<double>(), C.dir.as<double>()));
   }
   return B200_OK;
 }
 
 // ================================================================ outer solver
 // (both settings are the same on every rank of a slab run; everything that can
-// differ between ranks is agreed on collectively inside b200_amg_pcg).  On slabs the
-// block-wise multigrid is correct but not competitive yet -- without coarse levels
-// that span the ranks the slab interfaces cost ~4x the iterations (129 vs 35 on two
-// slabs of a 48x24x24 lattice; 200^3 on two GPUs: 258 ms against 213 ms for
-// Jacobi-PCG and 93 ms on one GPU) -- so it is opt-in (B200_AMG_SLABS=1) and slab
-// runs stay with Jacobi-PCG by default.
+// differ between ranks is agreed on collectively inside b200_amg_pcg / amg_setup)
 bool b200_amg_applicable(b200_ctx* ctx) {
   if (ctx->precond != B200_PRECOND_AMG || ctx->nonsym) return false;
   if (ctx->nranks == 1) return true;
-  const char* e = getenv("B200_AMG_SLABS");
-  return e && e[0] == '1';
+  const char* e = getenv("B200_AMG_SLABS");      // =0: slab runs stay with Jacobi-PCG
+  return !(e && e[0] == '0');
 }
 
 // returns B200_OK with *used = 0 when the hierarchy could not be built (coarsening
@@ -1050,15 +1345,14 @@ int b200_amg_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol, int6
                  double* x, int64_t* iters, double* relres, int* info, int* used) {
   *used = 0;
   // Slab mode (one rank per GPU): the outer flexible CG runs on the global operator
-  // (halo exchange + all-reduced dot products, as in the PCG) and every rank uses the
-  // hierarchy of the rows and columns it owns as its preconditioner -- additive
-  // Schwarz without overlap, no communication inside a cycle (the cycle's operands
-  // have zero halo pads, so its fine-level products see the local block only).
+  // (halo exchange + all-reduced dot products, as in the PCG) and the preconditioner is
+  // one multigrid cycle of the row-partitioned hierarchy (see the header).
   const bool multi = ctx->nranks > 1;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   RET(b200_pcg_prepare(ctx, ctx->force_fmt));
   // every rank must take the same path: agree on the local verdicts
-  int64_t bad = (!ctx->unit_diag || ctx->n <= AMG_COARSEST || ctx->n >= (1ll << 31)) ? 1 : 0;
+  const int64_t n_all = multi ? ctx->n_global : ctx->n;
+  int64_t bad = (!ctx->unit_diag || n_all <= AMG_COARSEST || n_all >= (1ll << 31)) ? 1 : 0;
   RET(b200_allreduce_max_host(ctx, &bad));
   if (bad) return B200_OK;
   AmgState* A = amg_of(ctx);
@@ -1219,8 +1513,7 @@ extern "C" int b200_amg_setup(b200_ctx* ctx, int* nlevels) {
     if (ctx) ctx->err = "amg_setup: no system matrix";
     return B200_ERR_ARG;
   }
-  if (ctx->nonsym || ctx->nranks > 1)
-    FAIL(B200_ERR_ARG, "amg: symmetric single-GPU systems only");
+  if (ctx->nonsym) FAIL(B200_ERR_ARG, "amg: symmetric systems only");
   CK(cudaSetDevice(ctx->device));
   RET(b200_pcg_prepare(ctx, ctx->force_fmt));
   RET(amg_setup(ctx));
@@ -1237,6 +1530,24 @@ extern "C" int b200_amg_level_shape(b200_ctx* ctx, int level, int64_t* n, int64_
   return B200_OK;
 }
 
+extern "C" int b200_amg_level_info(b200_ctx* ctx, int level, int64_t* out8) {
+  if (!ctx || !ctx->amg || !out8) return B200_ERR_ARG;
+  AmgState* A = amg_of(ctx);
+  if (level < 0 || level >= (int)A->nlev) FAIL(B200_ERR_ARG, "amg: no such level");
+  const AmgLevel& L = A->lv[level];
+  out8[0] = L.n;
+  out8[1] = L.nnz;
+  out8[2] = L.ng;
+  out8[3] = L.goff;
+  out8[4] = L.dist ? 1 : 0;
+  out8[5] = L.wlo;
+  out8[6] = L.whi;
+  out8[7] = (level + 1 < (int)A->nlev) ? L.coff : 0;
+  return B200_OK;
+}
+
+// Slab runs: rows are the ones this rank owns; column ids and the aggregation map are
+// exported in GLOBAL numbering, so that the ranks' parts stack to the global level.
 extern "C" int b200_amg_export_level(b200_ctx* ctx, int level, int32_t* indptr, int32_t* indices,
                                      double* data, int32_t* agg) {
   if (!ctx || !ctx->amg) return B200_ERR_ARG;
@@ -1248,17 +1559,20 @@ extern "C" int b200_amg_export_level(b200_ctx* ctx, int level, int32_t* indptr, 
   if (indptr)
     CK(cudaMemcpyAsync(indptr, L.ip, (size_t)(L.n + 1) * sizeof(int), cudaMemcpyDeviceToDevice,
                        ctx->stream));
-  if (indices)
-    CK(cudaMemcpyAsync(indices, L.ix, (size_t)L.nnz * sizeof(int), cudaMemcpyDeviceToDevice,
-                       ctx->stream));
+  if (indices) {
+    // level 0 already holds global ids; row-partitioned coarse levels local signed ones
+    const int add = (L.dist && level > 0) ? (int)L.goff : 0;
+    LAUNCH(ctx, k_amg_shift_ids, grid_for(L.nnz, AMG_T), AMG_T, 0, L.nnz, L.ix, add, 0, indices);
+  }
   if (data)
     CK(cudaMemcpyAsync(data, L.av, (size_t)L.nnz * sizeof(double), cudaMemcpyDeviceToDevice,
                        ctx->stream));
   if (agg) {
     if (level + 1 >= (int)A->nlev) FAIL(B200_ERR_ARG, "amg: the last level has no aggregation");
-    CK(cudaMemcpyAsync(agg, L.agg.p, (size_t)L.n * sizeof(int), cudaMemcpyDeviceToDevice,
-                       ctx->stream));
+    LAUNCH(ctx, k_amg_shift_ids, grid_for(L.n, AMG_T), AMG_T, 0, L.n, L.agg.as<int>(),
+           L.dist ? (int)L.coff : 0, 1, agg);
   }
+  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));
   return B200_OK;
 }

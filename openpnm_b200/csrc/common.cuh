@@ -146,6 +146,7 @@ struct b200_ctx {
   DevBuf w_cnt, w_keys, w_scan, w_part, w_ticket, w_flags, w_tmp0, w_tmp1, w_tmp2;
   int* flags_h = nullptr;      // pinned
   DevBuf h_row, h_col, h_dat, h_vec;   // device staging of b200_solve_coo_h
+  DevBuf w_coll;                       // staging of the small host-visible collectives (dist.cu)
 
   // preconditioner: B200_PRECOND_JACOBI or B200_PRECOND_AMG (amg.cu owns `amg`)
   int precond = 0;
@@ -264,6 +265,11 @@ int b200_halo_exchange_begin(b200_ctx* ctx, double* base);     // on comm_stream
 int b200_halo_exchange_end(b200_ctx* ctx);                     // stream waits for it
 int b200_allreduce_sum(b200_ctx* ctx, double* dev, int count); // in place, fp64
 int b200_allreduce_max_host(b200_ctx* ctx, int64_t* v);
+int b200_allreduce_sum_n(b200_ctx* ctx, double* dev, size_t count);
+int b200_allreduce_sum_i32(b200_ctx* ctx, int* dev, size_t count);
+int b200_halo_exchange_w(b200_ctx* ctx, void* owned, int64_t n, int elem_bytes, int64_t wlo,
+                         int64_t whi, int64_t slo, int64_t shi);
+int b200_allgather_i64_host(b200_ctx* ctx, const int64_t* mine, int k, int64_t* all);
 void b200_comm_release(b200_ctx* ctx);
 // solver.cu helpers used by transient.cu / bicgstab.cu
 int b200_spmv_dots(b200_ctx* ctx, const double* w_owned, const double* rv_owned,

@@ -151,6 +151,66 @@ int b200_allreduce_sum(b200_ctx* ctx, double* dev, int count) {
   return B200_OK;
 }
 
+// Vectors that every rank fills on its own segment and leaves zero elsewhere: the sum
+// over ranks IS the concatenation (x + 0 is exact), i.e. an all-gather with uneven
+// counts that needs no displacement bookkeeping.  amg.cu uses these to replicate the
+// small coarse levels of the multigrid on every rank.
+int b200_allreduce_sum_n(b200_ctx* ctx, double* dev, size_t count) {
+  if (ctx->nranks == 1 || count == 0) return B200_OK;
+  NCK(g_nccl.AllReduce(dev, dev, count, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
+  return B200_OK;
+}
+
+int b200_allreduce_sum_i32(b200_ctx* ctx, int* dev, size_t count) {
+  if (ctx->nranks == 1 || count == 0) return B200_OK;
+  NCK(g_nccl.AllReduce(dev, dev, count, ncclInt32, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
+  return B200_OK;
+}
+
+// Halo windows of unequal widths (coarse multigrid levels): `owned` points at the
+// first owned entry of a vector laid out [wlo | n | whi]; this rank receives wlo
+// entries from rank-1 and whi from rank+1 and sends its first slo / last shi owned
+// entries to them (slo == rank-1's whi, shi == rank+1's wlo: agreed on at setup).
+int b200_halo_exchange_w(b200_ctx* ctx, void* owned, int64_t n, int elem_bytes, int64_t wlo,
+                         int64_t whi, int64_t slo, int64_t shi) {
+  if (ctx->nranks == 1) return B200_OK;
+  if (wlo + whi + slo + shi == 0) return B200_OK;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl;
+  const ncclDataType_t ty = elem_bytes == 8 ? ncclDouble : ncclInt32;
+  char* o = static_cast<char*>(owned);
+  const int64_t eb = elem_bytes;
+  NCK(g_nccl.GroupStart());
+  if (ctx->rank > 0) {
+    if (slo > 0) NCK(g_nccl.Send(o, (size_t)slo, ty, ctx->rank - 1, comm, ctx->stream));
+    if (wlo > 0) NCK(g_nccl.Recv(o - wlo * eb, (size_t)wlo, ty, ctx->rank - 1, comm, ctx->stream));
+  }
+  if (ctx->rank < ctx->nranks - 1) {
+    if (shi > 0)
+      NCK(g_nccl.Send(o + (n - shi) * eb, (size_t)shi, ty, ctx->rank + 1, comm, ctx->stream));
+    if (whi > 0) NCK(g_nccl.Recv(o + n * eb, (size_t)whi, ty, ctx->rank + 1, comm, ctx->stream));
+  }
+  NCK(g_nccl.GroupEnd());
+  return B200_OK;
+}
+
+// k int64 per rank -> all[nranks * k] on the host of every rank (one synchronisation)
+int b200_allgather_i64_host(b200_ctx* ctx, const int64_t* mine, int k, int64_t* all) {
+  if (ctx->nranks == 1) {
+    for (int i = 0; i < k; ++i) all[i] = mine[i];
+    return B200_OK;
+  }
+  const size_t tot = (size_t)ctx->nranks * k;
+  CK(ctx->w_coll.ensure(tot * sizeof(long long)));
+  long long* d = ctx->w_coll.as<long long>();
+  CK(cudaMemsetAsync(d, 0, tot * sizeof(long long), ctx->stream));
+  CK(cudaMemcpyAsync(d + (size_t)ctx->rank * k, mine, (size_t)k * sizeof(long long),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  NCK(g_nccl.AllReduce(d, d, tot, ncclInt64, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
+  CK(cudaMemcpyAsync(all, d, tot * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
 int b200_allreduce_max_host(b200_ctx* ctx, int64_t* v) {
   if (ctx->nranks == 1) return B200_OK;
   CK(ctx->w_tmp2.ensure(64));

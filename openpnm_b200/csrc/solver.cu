@@ -419,6 +419,18 @@ static int prepare_operator(b200_ctx* ctx) {
     FAIL(B200_ERR_ARG, "DIA format forced but the matrix has more than %d diagonals",
          B200_MAX_DIAGS);
   if (ctx->force_fmt == B200_FMT_DIA) want_dia = true;
+  // slab runs: the format (and, below, the scaling) decides which communication path
+  // the iteration takes, so the ranks must agree on it -- one rank on the NCCL path
+  // while the others wait on their mailboxes would hang
+  {
+    int64_t no_dia = want_dia ? 0 : 1;
+    RET(b200_allreduce_max_host(ctx, &no_dia));
+    if (no_dia) {
+      if (ctx->force_fmt == B200_FMT_DIA)
+        FAIL(B200_ERR_ARG, "DIA format forced but a rank cannot use it");
+      want_dia = false;
+    }
+  }
   int64_t halo = (want_dia || ctx->nranks > 1) ? tab.maxband : 0;
   RET(b200_allreduce_max_host(ctx, &halo));         // every rank uses the same halo width
   int64_t nmin = n;
@@ -443,7 +455,11 @@ static int prepare_operator(b200_ctx* ctx) {
   CK(cudaMemcpyAsync(ctx->flags_h, flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost,
                      ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->unit_diag = !ctx->flags_h[FLAG_NONPOS_DIAG];
+  {
+    int64_t nonpos = ctx->flags_h[FLAG_NONPOS_DIAG] ? 1 : 0;   // agreed on by all ranks
+    RET(b200_allreduce_max_host(ctx, &nonpos));
+    ctx->unit_diag = !nonpos;
+  }
   if (!ctx->unit_diag) {
     // indefinite / semi-definite diagonal: no scaling, explicit diagonal, CSR
     LAUNCH(ctx, k_scale, grid_for(n, 256), 256, 0, cur_diag(ctx), n, 0, s_owned, flags);
@@ -471,7 +487,9 @@ static int prepare_operator(b200_ctx* ctx) {
       CK(cudaMemcpyAsync(ctx->flags_h, flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost,
                          ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
-      if (ctx->flags_h[FLAG_NONSYM]) want_dia = false;
+      int64_t nonsym = ctx->flags_h[FLAG_NONSYM] ? 1 : 0;
+      RET(b200_allreduce_max_host(ctx, &nonsym));
+      if (nonsym) want_dia = false;
     }
     if (want_dia) {
       ctx->dia.nd = tab.n;

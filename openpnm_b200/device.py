@@ -253,6 +253,15 @@ class Context:
             out.append((n.value, nnz.value))
         return out
 
+    def amg_level_info(self, level):
+        """dict(n, nnz, n_global, first_row, partitioned, halo_lo, halo_hi, coarse_offset)
+        of one level of the hierarchy (slab runs: what this rank holds)."""
+        out = (C.c_int64 * 8)()
+        self._ck(self.lib.b200_amg_level_info(self._h, int(level), out))
+        keys = ("n", "nnz", "n_global", "first_row", "partitioned", "halo_lo", "halo_hi",
+                "coarse_offset")
+        return dict(zip(keys, (int(v) for v in out)))
+
     def amg_export_level(self, level, with_agg=True):
         """(indptr, indices, data, agg) device tensors of one level (agg None if
         the level is the last one)."""
