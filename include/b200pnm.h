@@ -109,6 +109,47 @@ int b200_check_topology(b200_ctx* ctx, const int64_t* conns, int64_t Nt,
                         const double* bc_rate, int64_t* n_clusters,
                         int64_t* n_without_bc);
 
+/* Cluster labels (labels[i] = smallest pore index of pore i's cluster; device, Np
+ * int32) -- `csgraph.connected_components` in topotools/_topotools.py:1014 and
+ * models/network/_health.py:55-62.                                           */
+int b200_cluster_labels(b200_ctx* ctx, const int64_t* conns, int64_t Nt,
+                        int64_t Np, int32_t* labels, int64_t* n_clusters);
+
+/* The same health check in a slab run: `conns` are the throats touching this
+ * rank's rows [row_begin,row_end) (global pore ids), `halo` the network's index
+ * bandwidth max|c1-c0|.  Clusters that stay away from the two cut regions
+ * [row_begin-halo,row_begin+halo) and [row_end-halo,row_end+halo) are complete
+ * and judged here (*interior_without_bc); for the pores of the cut regions the
+ * local cluster label and its has-a-BC-pore mark are exported (device,
+ * 4*halo entries each: low region then high region, -1 outside the network) so
+ * that the host can join clusters across ranks (openpnm_b200/dist.py).       */
+int b200_slab_clusters(b200_ctx* ctx, const int64_t* conns, int64_t Nt,
+                       int64_t Np, int64_t row_begin, int64_t row_end,
+                       int64_t halo, const double* bc_value,
+                       const double* bc_rate, int32_t* win_labels,
+                       uint8_t* win_has_bc, int64_t* interior_without_bc);
+
+/* ------------------------------------------ network health + trim (f-2)
+ * Replaces utils.check_network_health (openpnm/utils/_health.py:40-98) with the
+ * models it calls (openpnm/models/network/_health.py:11-76): per pore the size
+ * of its cluster and whether it is isolated (no throat touches it), per throat
+ * whether it loops back onto its own pore; any output may be NULL.
+ * counts6_h (host) = {clusters, isolated pores, pores outside the largest
+ * cluster ('disconnected_pores'), looped throats, 0, size of the largest
+ * cluster}.  Throats pointing at non-existent pores are B200_ERR_INDEX.
+ * b200_trim replaces topotools.trim (openpnm/topotools/_topotools.py:157-229):
+ * pores with pore_keep == 0 go together with every throat touching them,
+ * throats with throat_keep == 0 (NULL: keep all) too; survivors keep their
+ * order.  pore_map / throat_map (device, int64): new index or -1; conns_out
+ * (device, room for Nt pairs): the remapped connections of the kept throats. */
+int b200_network_health(b200_ctx* ctx, const int64_t* conns, int64_t Nt,
+                        int64_t Np, int32_t* cluster_size, uint8_t* isolated,
+                        uint8_t* looped, int32_t* labels, int64_t* counts6_h);
+int b200_trim(b200_ctx* ctx, const int64_t* conns, int64_t Nt, int64_t Np,
+              const uint8_t* pore_keep, const uint8_t* throat_keep,
+              int64_t* pore_map, int64_t* throat_map, int64_t* conns_out,
+              int64_t* Np_new, int64_t* Nt_new);
+
 /* ------------------------------------------------ K2: boundary conditions
  * Replaces Transport._build_b + _apply_BCs (_transport.py:117-121,145-169).
  * bc_value / bc_rate: (Np,) f64 for ALL pores (global indexing), NaN = no BC;

@@ -58,6 +58,10 @@ SIGNATURES = {
     "b200_build_laplacian2": (C.c_int, [_p, _p, _p, _i64, _i64, _pi64]),
     "b200_add_to_diagonal": (C.c_int, [_p, _p]),
     "b200_check_topology": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _pi64, _pi64]),
+    "b200_cluster_labels": (C.c_int, [_p, _p, _i64, _i64, _p, _pi64]),
+    "b200_slab_clusters": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _pi64]),
+    "b200_network_health": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _pi64]),
+    "b200_trim": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p, _pi64, _pi64]),
     "b200_apply_bcs": (C.c_int, [_p, _p, _p, C.c_int, _pdbl, _pi64]),
     "b200_pure_diag_sum": (C.c_int, [_p, _pdbl, _pi64]),
     "b200_set_diag_mean": (C.c_int, [_p, _dbl]),

@@ -393,33 +393,27 @@ class Transport(dict):
         import torch.distributed as dist
         from . import dist as bdist
         world, rank = dist.get_world_size(), dist.get_rank()
-        conns = np.asarray(self.network["throat.conns"], dtype=np.int64)
         g = self._conductance()
-        band = bdist.bandwidth(conns)
-        shape = getattr(self.network, "shape", None)
-        if shape is not None and len(shape) == 3 and int(np.prod(shape)) == self.Np:
-            ranges = bdist.cubic_slab_ranges(shape, world)
-        else:
-            ranges = bdist.slab_ranges(self.Np, world)
-        if min(e - b for b, e in ranges) < band:
-            raise Exception(f"a slab would be thinner than the matrix half-bandwidth ({band}); "
-                            "renumber the pores by coordinate (openpnm_b200.dist.coordinate_order) "
-                            "or use fewer ranks")
-        rb, re = ranges[rank]
+        rb, re, band, sel, conns_loc = self._slab_plan(world, rank)
         key = (id(self.network), world, rank, solver.device, solver.fmt)
         ss = getattr(solver, "_slab", None)
         if ss is None or getattr(solver, "_slab_key", None) != key:
             ss = bdist.SlabSolver(self.Np, rb, re, device=solver.device, fmt=solver.fmt)
             solver._slab, solver._slab_key, solver._slab_p2p = ss, key, None
         ctx = ss.ctx
+        ctx.set_precond(getattr(solver, "precond", "jacobi"))
         self._ctx, self._slab = ctx, ss
+        conns_dev = ctx.to_device(conns_loc, torch.int64)      # this rank's throats only
         if self.settings["validate_topology"]:
-            self._validate_topology_health(ctx)
-        mask = bdist.slab_throat_mask(conns, rb, re)
+            # every rank labels the clusters of its own throats on its GPU; the cut
+            # regions are joined on the host (dist.slab_topology_check)
+            if bdist.slab_topology_check(ctx, conns_dev, self.Np, rb, re, band,
+                                         self["pore.bc.value"], self["pore.bc.rate"]):
+                raise Exception("Your network is clustered, making Ax = b ill-conditioned")
         self._update_hook(None)        # raises if a model needs the host (single-GPU only)
         try:
             srcs = self._sources()
-            f, nnz0, nnz = ss.assemble(conns[mask], g[mask], self["pore.bc.value"],
+            f, nnz0, nnz = ss.assemble(conns_dev, g[sel], self["pore.bc.value"],
                                        self["pore.bc.rate"], keep_zero_diag=len(srcs) > 0)
             ctx.clear_sources()
             if solver._slab_p2p is None:              # maps the peers once (source-free operator)
@@ -453,6 +447,44 @@ class Transport(dict):
         self.stats = ctx.stats()
         self.soln.relres = self.stats["relres"]
         self._post_run(x)
+
+    def _slab_plan(self, world, rank):
+        """(row_begin, row_end, index bandwidth, selector of this rank's throats, their
+        conns), cached per (network, world, rank).  A lattice made by this package's
+        `Cubic` gets its slab's throats from index arithmetic (dist.cubic_slab_throats):
+        no rank ever touches the full 191 M-throat list of a 400^3 network; any other
+        network is masked once."""
+        from . import dist as bdist
+        from .network import Cubic
+        net = self.network
+        key = (id(net), net.Nt, world, rank)
+        plan = getattr(self, "_slab_plan_cache", None)
+        if plan is not None and plan[0] == key:
+            return plan[1]
+        shape = getattr(net, "shape", None)
+        lattice = shape is not None and len(shape) == 3 and int(np.prod(shape)) == self.Np
+        ranges = bdist.cubic_slab_ranges(shape, world) if lattice else \
+            bdist.slab_ranges(self.Np, world)
+        rb, re = ranges[rank]
+        nx, ny, nz = (int(v) for v in shape) if lattice else (0, 0, 0)
+        analytic = type(net) is Cubic and lattice and \
+            net.Nt == (nx - 1) * ny * nz + nx * (ny - 1) * nz + nx * ny * (nz - 1) and \
+            not getattr(net, "_conns_touched", False)
+        if analytic:
+            band = ny * nz if nx > 1 else (nz if ny > 1 else 1)
+            sel, conns_loc = bdist.cubic_slab_throats(shape, rb // (ny * nz), re // (ny * nz))
+        else:
+            conns = np.asarray(net["throat.conns"], dtype=np.int64)
+            band = bdist.bandwidth(conns)
+            sel = np.flatnonzero(bdist.slab_throat_mask(conns, rb, re))
+            conns_loc = conns[sel]
+        if min(e - b for b, e in ranges) < band:
+            raise Exception(f"a slab would be thinner than the matrix half-bandwidth ({band}); "
+                            "renumber the pores by coordinate (openpnm_b200.dist.coordinate_order) "
+                            "or use fewer ranks")
+        out = (rb, re, band, sel, conns_loc)
+        self._slab_plan_cache = (key, out)
+        return out
 
     def _download(self, ctx, x_dev):
         """Device -> host through a page-locked staging buffer (kept per size)."""

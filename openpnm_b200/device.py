@@ -154,6 +154,70 @@ class Context:
                                               C.byref(nb)))
         return nc.value, nb.value
 
+    def cluster_labels(self, conns, Np):
+        """(labels int32 device tensor: smallest pore index of each pore's cluster, n_clusters)"""
+        torch = _torch()
+        conns = self.to_device(conns, torch.int64)
+        lab = self.empty(Np, torch.int32)
+        nc = C.c_int64()
+        self._ck(self.lib.b200_cluster_labels(self._h, self._p(conns), int(conns.numel() // 2),
+                                              int(Np), self._p(lab), C.byref(nc)))
+        return self._publish(lab), nc.value
+
+    def slab_clusters(self, conns_local, Np, row_begin, row_end, halo, bc_value=None, bc_rate=None):
+        """Per-rank part of the slab topology check: (labels of the two cut regions,
+        their has-BC marks, number of complete clusters without a BC pore)."""
+        torch = _torch()
+        conns = self.to_device(conns_local, torch.int64)
+        bv = self.to_device(bc_value, torch.float64) if bc_value is not None else None
+        br = self.to_device(bc_rate, torch.float64) if bc_rate is not None else None
+        lab = self.empty(max(4 * int(halo), 1), torch.int32)
+        hb = self.empty(max(4 * int(halo), 1), torch.uint8)
+        bad = C.c_int64()
+        self._ck(self.lib.b200_slab_clusters(self._h, self._p(conns), int(conns.numel() // 2),
+                                             int(Np), int(row_begin), int(row_end), int(halo),
+                                             self._p(bv), self._p(br), self._p(lab), self._p(hb),
+                                             C.byref(bad)))
+        self._publish(lab, hb)
+        return lab[:4 * int(halo)], hb[:4 * int(halo)], bad.value
+
+    def network_health(self, conns, Np, want_arrays=True):
+        """check_network_health on the device: dict of counts + device arrays
+        (cluster_size int32, isolated uint8, looped uint8, labels int32)."""
+        torch = _torch()
+        conns = self.to_device(conns, torch.int64)
+        Nt = int(conns.numel() // 2)
+        cs = self.empty(Np, torch.int32) if want_arrays else None
+        iso = self.empty(Np, torch.uint8) if want_arrays else None
+        lp = self.empty(max(Nt, 1), torch.uint8) if want_arrays else None
+        lab = self.empty(Np, torch.int32) if want_arrays else None
+        cnt = (C.c_int64 * 6)()
+        self._ck(self.lib.b200_network_health(self._h, self._p(conns), Nt, int(Np), self._p(cs),
+                                              self._p(iso), self._p(lp), self._p(lab), cnt))
+        if want_arrays:
+            self._publish(cs, iso, lp, lab)
+        return dict(n_clusters=int(cnt[0]), n_isolated=int(cnt[1]), n_disconnected=int(cnt[2]),
+                    n_looped=int(cnt[3]), largest_cluster=int(cnt[5]), cluster_size=cs,
+                    isolated=iso, looped=None if lp is None else lp[:Nt], labels=lab)
+
+    def trim(self, conns, Np, pore_keep, throat_keep=None):
+        """topotools.trim on the device: (conns_new (Nt_new,2) int64 device, pore_map,
+        throat_map, Np_new)."""
+        torch = _torch()
+        conns = self.to_device(conns, torch.int64)
+        Nt = int(conns.numel() // 2)
+        pk = self.to_device(pore_keep, torch.uint8)
+        tk = self.to_device(throat_keep, torch.uint8) if throat_keep is not None else None
+        pmap = self.empty(Np, torch.int64)
+        tmap = self.empty(max(Nt, 1), torch.int64)
+        out = self.empty(max(2 * Nt, 2), torch.int64)
+        npn, ntn = C.c_int64(), C.c_int64()
+        self._ck(self.lib.b200_trim(self._h, self._p(conns), Nt, int(Np), self._p(pk), self._p(tk),
+                                    self._p(pmap), self._p(tmap), self._p(out), C.byref(npn),
+                                    C.byref(ntn)))
+        self._publish(pmap, tmap, out)
+        return out[:2 * ntn.value].view(-1, 2), pmap, tmap[:Nt], npn.value
+
     def apply_bcs(self, bc_value=None, bc_rate=None, keep_zero_diag=False):
         torch = _torch()
         bv = self.to_device(bc_value, torch.float64) if bc_value is not None else None

@@ -21,7 +21,8 @@ import os
 import numpy as np
 
 __all__ = ["slab_ranges", "cubic_slab_ranges", "slab_throat_mask", "cubic_slab_throats",
-           "bandwidth", "coordinate_order", "SlabSolver", "init_process_group"]
+           "bandwidth", "coordinate_order", "SlabSolver", "init_process_group",
+           "slab_topology_check", "join_slab_clusters"]
 
 
 # ------------------------------------------------------------ host-side plan
@@ -113,6 +114,64 @@ def coordinate_order(coords, axis=0):
     inv = np.empty_like(perm)
     inv[perm] = np.arange(perm.size)
     return perm, inv
+
+
+def join_slab_clusters(parts, Np):
+    """Host half of the slab topology check.  parts[r] = (labels, has_bc, interior_bad)
+    of rank r (b200_slab_clusters): labels / has-BC marks of the pores of rank r's two
+    cut regions (2*halo entries each, index-aligned with the neighbour's: rank r's high
+    region and rank r+1's low region are the same pores).  Two local clusters that
+    label the same pore are one cluster; returns the number of clusters (complete ones
+    + joined ones) that contain no BC pore -- what `is_fully_connected` tests
+    (openpnm/topotools/_topotools.py:993-1024).  Tiny: O(halo * ranks) integers."""
+    import scipy.sparse as sprs
+    from scipy.sparse import csgraph
+    bad = int(sum(int(p[2]) for p in parts))
+    keys, flags, ea, eb = [], [], [], []
+    for r, (lab, hb, _) in enumerate(parts):
+        lab = np.asarray(lab).astype(np.int64)
+        ok = lab >= 0
+        keys.append(r * np.int64(Np) + lab[ok])
+        flags.append(np.asarray(hb)[ok].astype(bool))
+        if r + 1 < len(parts):
+            h2 = lab.size // 2
+            hi = lab[h2:]
+            lo = np.asarray(parts[r + 1][0]).astype(np.int64)[:h2]
+            both = (hi >= 0) & (lo >= 0)
+            ea.append(r * np.int64(Np) + hi[both])
+            eb.append((r + 1) * np.int64(Np) + lo[both])
+    keys = np.concatenate(keys) if keys else np.zeros(0, dtype=np.int64)
+    if keys.size == 0:
+        return bad
+    flags = np.concatenate(flags)
+    nodes, inv = np.unique(keys, return_inverse=True)
+    node_bc = np.zeros(nodes.size, dtype=bool)
+    np.logical_or.at(node_bc, inv, flags)
+    if ea:
+        a = np.searchsorted(nodes, np.concatenate(ea))
+        b = np.searchsorted(nodes, np.concatenate(eb))
+    else:
+        a = b = np.zeros(0, dtype=np.int64)
+    g = sprs.coo_matrix((np.ones(a.size, dtype=np.int8), (a, b)), shape=(nodes.size, nodes.size))
+    ncomp, comp = csgraph.connected_components(g, directed=False)
+    comp_bc = np.zeros(ncomp, dtype=bool)
+    np.logical_or.at(comp_bc, comp, node_bc)
+    return bad + int((~comp_bc).sum())
+
+
+def slab_topology_check(ctx, conns_local, Np, row_begin, row_end, halo, bc_value, bc_rate):
+    """`_validate_topology_health` of a slab run (collective): every rank labels the
+    clusters of the throats it holds on its GPU, the cut regions are joined on the
+    host.  Returns the number of clusters without a BC pore."""
+    import torch.distributed as dist
+    lab, hb, bad = ctx.slab_clusters(conns_local, Np, row_begin, row_end, halo, bc_value, bc_rate)
+    ctx.synchronize()
+    part = (lab.cpu().numpy(), hb.cpu().numpy(), bad)
+    parts = [part]
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        parts = [None] * dist.get_world_size()
+        dist.all_gather_object(parts, part)
+    return join_slab_clusters(parts, Np)
 
 
 # --------------------------------------------------------------- processes

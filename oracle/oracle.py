@@ -433,3 +433,41 @@ def rate(conns, g, x, pores=None, throats=None, mode="group"):
     if mode == "group":
         R = np.sum(R)
     return np.array(R, ndmin=1)
+
+
+# ---------------------------------------------------------------- health + trim
+def network_health(conns, Np):
+    """check_network_health restricted to what the path needs
+    (openpnm/utils/_health.py:40-98; models/network/_health.py:44-76): per-pore cluster
+    size (scipy connected_components on the triu adjacency), isolated pores
+    (np.unique(conns) misses them), pores outside the largest cluster, looped throats."""
+    from scipy.sparse import csgraph
+    conns = np.asarray(conns, dtype=np.int64).reshape(-1, 2)
+    am = sprs.coo_matrix((np.ones(conns.shape[0], dtype=np.int8), (conns[:, 0], conns[:, 1])),
+                         shape=(Np, Np))
+    ncomp, cluster_num = csgraph.connected_components(am, directed=False)
+    _, ind, N = np.unique(cluster_num, return_inverse=True, return_counts=True)
+    size = N[ind]
+    isolated = np.ones(Np, dtype=bool)
+    isolated[np.unique(conns)] = False
+    return {"cluster_size": size, "isolated": isolated, "n_clusters": int(ncomp),
+            "disconnected": np.flatnonzero(size < size.max()),
+            "looped": np.flatnonzero(conns[:, 0] == conns[:, 1]),
+            "cluster_num": cluster_num}
+
+
+def trim(conns, Np, pores=(), throats=()):
+    """topotools.trim (openpnm/topotools/_topotools.py:157-229): returns the remapped
+    conns of the kept throats, the kept pore indices and the kept throat indices."""
+    conns = np.asarray(conns, dtype=np.int64).reshape(-1, 2)
+    Pkeep = np.ones(Np, dtype=bool)
+    Tkeep = np.ones(conns.shape[0], dtype=bool)
+    if np.size(pores):
+        Pkeep[np.asarray(pores)] = False
+        Tkeep[~(Pkeep[conns[:, 0]] & Pkeep[conns[:, 1]])] = False   # find_neighbor_throats(union)
+    if np.size(throats):
+        Tkeep[np.asarray(throats)] = False
+    Pmap = -np.ones(Np, dtype=np.int64)
+    Pmap[Pkeep] = np.arange(Pkeep.sum())
+    new = np.stack([Pmap[conns[Tkeep, 0]], Pmap[conns[Tkeep, 1]]], axis=1)
+    return new, np.flatnonzero(Pkeep), np.flatnonzero(Tkeep)

@@ -133,6 +133,75 @@ def main():
     if rank == 0:
         print(f"dist ok reactive world={world} num_iter={rt.soln.num_iter} err={errp:.2e}",
               flush=True)
+    # ---- multigrid through the algorithm API (one hierarchy across the slabs)
+    shape = (32, 12, 12)
+    pn = b2.Cubic(shape, spacing=1e-4)
+    ph = b2.Phase(pn)
+    g = 10.0 ** np.random.default_rng(6).uniform(-15, -12, pn.Nt)
+    ph["throat.hydraulic_conductance"] = g
+    sf = b2.StokesFlow(network=pn, phase=ph)
+    sf.set_value_BC(pores=pn.pores("left"), values=2e5)
+    sf.set_value_BC(pores=pn.pores("right"), values=1e5)
+    sf.run(solver=b2.B200PCG(tol=1e-13))
+    it_jacobi = sf.soln.cg_iters
+    sf.run(solver=b2.B200PCG(tol=1e-13, precond="amg"))
+    ref = oracle.transport_run(pn.conns, g, pn.Np, bc_value=sf["pore.bc.value"])
+    err = np.max(np.abs(sf.x - ref["x"]) / np.abs(ref["x"]))
+    assert sf.soln.is_converged and err < 1e-8, err
+    assert sf.soln.cg_iters < it_jacobi / 3, (sf.soln.cg_iters, it_jacobi)
+    if rank == 0:
+        print(f"dist ok algorithm-API multigrid world={world} err={err:.2e} "
+              f"iters={sf.soln.cg_iters} (jacobi {it_jacobi})", flush=True)
+    # ---- topology check of a slab run: a block cut off from every BC pore is refused
+    cut = ~((pn.conns[:, 0] // 144 == 19) & (pn.conns[:, 1] // 144 == 20))
+    pn2 = b2.Network(conns=pn.conns[cut], Np=pn.Np)
+    ph2 = b2.Phase(pn2)
+    ph2["throat.hydraulic_conductance"] = g[cut]
+    sf2 = b2.StokesFlow(network=pn2, phase=ph2)
+    sf2["pore.bc.value"] = np.where(np.arange(pn.Np) < 144, 2e5, np.nan)
+    try:
+        sf2.run(solver=b2.B200PCG(tol=1e-10))
+        raise AssertionError("a clustered network was accepted")
+    except Exception as e:
+        assert "clustered" in str(e), e
+    sf2["pore.bc.value"][pn.Np - 1] = 1e5          # one BC pore in the far block: healthy
+    sf2.run(solver=b2.B200PCG(tol=1e-10))
+    assert sf2.soln.is_converged
+    if rank == 0:
+        print(f"dist ok slab topology check world={world}", flush=True)
+    # ---- irregular network: Delaunay, pores ordered by x, over-long throats cut, isolated
+    # pores and minor clusters trimmed on the device, then the slab-parallel solve
+    from openpnm_b200 import topotools
+    pts = np.random.default_rng(7).random((12000, 3))
+    pts = pts[bdist.coordinate_order(pts)[0]]
+    conns = oracle.delaunay_network(pts)
+    L = np.linalg.norm(pts[conns[:, 0]] - pts[conns[:, 1]], axis=1)
+    pn3 = b2.Network(coords=pts, conns=conns[L < 0.06])
+    hl = topotools.check_network_health(pn3, ctx=b2.B200PCG().ctx)
+    assert len(hl["disconnected_pores"]) > 0
+    topotools.trim(pn3, pores=hl["disconnected_pores"], ctx=b2.B200PCG().ctx)
+    g3 = 10.0 ** np.random.default_rng(8).uniform(-15, -12, pn3.Nt)
+    ph3 = b2.Phase(pn3)
+    ph3["throat.diffusive_conductance"] = g3
+    bcv = np.full(pn3.Np, np.nan)
+    bcv[pn3["pore.coords"][:, 0] < 0.05] = 1.0
+    bcv[pn3["pore.coords"][:, 0] > 0.95] = 0.0
+    ref = oracle.transport_run(pn3.conns, g3, pn3.Np, bc_value=bcv)
+    its = {}
+    for precond in ("jacobi", "amg"):
+        fd = b2.FickianDiffusion(network=pn3, phase=ph3)
+        fd["pore.bc.value"] = bcv
+        fd.run(solver=b2.B200PCG(tol=1e-13, precond=precond))
+        err = np.max(np.abs(fd.x - ref["x"]))
+        assert fd.soln.is_converged and err < 1e-8, (precond, err)
+        qi = fd.rate(pores=np.flatnonzero(bcv == 1.0))[0]
+        qo = fd.rate(pores=np.flatnonzero(bcv == 0.0))[0]
+        assert abs(qi + qo) <= 1e-8 * abs(qi)
+        its[precond] = fd.soln.cg_iters
+    assert its["amg"] < its["jacobi"] / 2, its
+    if rank == 0:
+        print(f"dist ok delaunay Np={pn3.Np} Nt={pn3.Nt} band={bdist.bandwidth(pn3.conns)} "
+              f"world={world} iters={its} fmt={fd._ctx.pcg_format()}", flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
