@@ -4,13 +4,20 @@ network (BASELINE.json: Cubic 400^3, 64M pores, Jacobi-PCG rtol 1e-10), on
 N B200s of one box.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--size 400]
-    python bench.py --impl reference ...      # CPU arm: oracle port + SciPy
+    python bench.py --impl reference ...      # CPU arm: unmodified OpenPNM + SciPy
 
 One "step" = one full pass of the hot path on the resident network:
 assemble the Laplacian from conns + g, apply the inlet/outlet Dirichlet BCs,
-Jacobi-PCG to rtol 1e-10, rate() through the inlet and outlet.  `value` has
-the inputs already in HBM; `e2e` goes through the public API
-(`StokesFlow.run`) from pinned HOST arrays and reads x back every step.
+Jacobi-PCG to rtol 1e-10.  `value` has the inputs already in HBM; `e2e` goes
+through the public API (`StokesFlow.run` + `rate`, under torchrun for N > 1) from
+pinned HOST arrays, topology check included, and reads x back every step.
+Next to it, in the same line:
+  amg     the same step with B200PCG(precond='amg') at every N (time-to-solve),
+  parity  the 1e-8 claim at this size: Jacobi-PCG and the multigrid solve at rtol
+          1e-12 and 1e-13 compared with each other (x, inlet/outlet rates, residual on
+          the canonical CSR) and, for N > 1, with a single-GPU solve made by rank 0,
+  matched the GPU arm on the reference arm's own (small) problem, for a same-problem
+          time ratio next to the rate ratio.
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -94,13 +101,19 @@ class ClockSampler:
         return out
 
 
+def pardiso_note():
+    try:
+        import pypardiso  # noqa: F401
+        return "pypardiso present"
+    except Exception:
+        return "Pardiso unavailable (pypardiso is not installed); SuperLU/ScipyCG used"
+
+
 # ------------------------------------------------------------------ CPU arm
 def cpu_solve_sample(n, rtol=RTOL):
-    """The reference's CPU path on a Cubic n^3 sample: numpy assembly exactly as
-    `_build_A`/`_apply_BCs` (oracle restatement) + SciPy CSR SpMV inside a
-    Jacobi-PCG with ScipyCG's stopping rule.  Returns dict with timings."""
+    """Fallback when the reference cannot be imported: the oracle port of its path
+    (numpy assembly as `_build_A`/`_apply_BCs` + SciPy CSR SpMV Jacobi-PCG)."""
     from oracle import oracle
-    t0 = time.perf_counter()
     net = oracle.cubic_network([n, n, n], spacing=1e-4)
     g = conductance(net["Nt"])
     bcv = np.full(net["Np"], np.nan)
@@ -109,13 +122,10 @@ def cpu_solve_sample(n, rtol=RTOL):
     t1 = time.perf_counter()
     A, b, f = oracle.apply_bcs(oracle.build_A(net["conns"], g, net["Np"]), net["Np"], bcv, None)
     M = oracle.to_csr(A, net["Np"])
-    t2 = time.perf_counter()
     x, info, its = oracle.jacobi_pcg(M, b, rtol=rtol)
-    t3 = time.perf_counter()
     q = oracle.rate(net["conns"], g, x, pores=net["labels"]["left"])[0]
     t4 = time.perf_counter()
-    return dict(Np=net["Np"], iters=its, info=info, t_gen=t1 - t0, t_assemble=t2 - t1,
-                t_solve=t3 - t2, t_rate=t4 - t3, t_step=t4 - t1, rate=q)
+    return dict(Np=net["Np"], iters=its, info=info, t_step=t4 - t1, rate=q)
 
 
 def reference_openpnm_sample(n, rtol=RTOL):
@@ -170,6 +180,7 @@ def reference_arm(args):
         threads = 1
     n = args.ref_size
     real = reference_openpnm_sample(min(n, 24))        # also the import probe / warm-up
+    rates = []
     if real is not None:
         for _ in range(max(args.warmup - 1, 0)):
             reference_openpnm_sample(min(n, 24))
@@ -177,11 +188,14 @@ def reference_arm(args):
         for _ in range(args.steps):
             r = reference_openpnm_sample(n)
             t.append(r["t_step"])
+            rates.append(r["rate"])
             its, Np = r["iters"], r["Np"]
-        kind = "reference"
+        kind, solver = "reference", f"ScipyCG(tol={RTOL:g}) (SciPy's unpreconditioned CG)"
         sample = (f"unmodified OpenPNM StokesFlow.run(solver=ScipyCG(tol={RTOL:g})) + rate() on "
-                  f"Cubic {n}^3 (same g distribution/BCs as the GPU arm's Cubic {args.size}^3): "
-                  f"its own topology check, 3 assemblies and SciPy's serial CG, {its} iterations")
+                  f"Cubic {n}^3 -- a bounded sample of the GPU arm's Cubic {args.size}^3 workload "
+                  f"(same g distribution, BCs and rtol; the full size would take the CPU hours): "
+                  f"its own topology check, 3 assemblies and SciPy's serial CG, {its} iterations. "
+                  + pardiso_note())
     else:
         n = args.cpu_size
         for _ in range(args.warmup):
@@ -190,20 +204,26 @@ def reference_arm(args):
         for _ in range(args.steps):
             r = cpu_solve_sample(n)
             t.append(r["t_step"])
+            rates.append(r["rate"])
             its, Np = r["iters"], r["Np"]
-        kind = "port"
-        sample = (f"Cubic {n}^3 StokesFlow (same g distribution/BCs/rtol as the GPU arm's Cubic "
-                  f"{args.size}^3): numpy assembly as the reference + SciPy CSR SpMV Jacobi-PCG, "
-                  f"{its} iterations; SciPy's SpMV and CG are serial")
+        kind, solver = "port", "oracle port: SciPy CSR SpMV Jacobi-PCG"
+        sample = (f"oracle port on Cubic {n}^3 -- a bounded sample of the GPU arm's Cubic "
+                  f"{args.size}^3 workload (same g distribution/BCs/rtol): numpy assembly as the "
+                  f"reference + SciPy CSR SpMV Jacobi-PCG, {its} iterations; serial. "
+                  + pardiso_note())
     ms = 1e3 * float(np.mean(t))
     val = Np * its / (ms * 1e-3)
+    cfg = workload_config(n, Np, 3 * n * n * (n - 1), {"solver": solver})
+    cfg["sample_of"] = f"Cubic {args.size}x{args.size}x{args.size} (the GPU arm's workload)"
+    cfg["size_solved"] = n
     line = {
         "impl": "reference", "metric": "stokesflow_dof_iter_per_s", "value": val,
         "unit": "DOF*iter/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.size, None, None, None),
-        "time_to_solve_s": ms * 1e-3,
+        "config": cfg,
+        "same_config": False,
+        "time_to_solve_s": ms * 1e-3, "cg_iters": its, "rate_inlet": float(np.mean(rates)),
         "cpu_baseline": {"value": val, "unit": "DOF*iter/s", "cores": 1, "kind": kind,
                          "blas_threads": threads, "sample": sample},
         "e2e": {"value": val, "unit": "DOF*iter/s", "h2d_bytes_per_step": 0,
@@ -213,24 +233,52 @@ def reference_arm(args):
     return 0
 
 
-def workload_config(size, Np, Nt, extra):
+def workload_config(size, Np, Nt, extra, solver="Jacobi-PCG"):
     cfg = {"workload": f"Cubic {size}x{size}x{size} StokesFlow (g=10^U(-15,-12) seed 0, "
-                       f"left={P_IN:g}/right={P_OUT:g} Dirichlet), Jacobi-PCG rtol {RTOL:g}",
+                       f"left={P_IN:g}/right={P_OUT:g} Dirichlet), rtol {RTOL:g}",
            "rtol": RTOL, "l2": "inputs larger than L2 (every PCG vector >= 4x the 126 MB L2 at "
                                "400^3); no flush needed"}
     if Np:
         cfg.update(Np=int(Np), Nt=int(Nt))
     if extra:
         cfg.update(extra)
+    cfg.setdefault("solver", solver)
     return cfg
 
 
 # ------------------------------------------------------------------ GPU arm
+def matched_leg(b2, n, steps):
+    """The GPU arm on the reference arm's own problem (Cubic n^3 through the public API,
+    host arrays in, x and rate out): one same-problem time next to the CPU's."""
+    import torch
+    pn = b2.Cubic([n, n, n], spacing=1e-4, coords=False)
+    ph = b2.Phase(pn)
+    ph["throat.hydraulic_conductance"] = conductance(pn.Nt)
+    out = {}
+    for precond in ("jacobi", "amg"):
+        sf = b2.StokesFlow(network=pn, phase=ph)
+        sf.set_value_BC(pores=pn.pores("left"), values=P_IN)
+        sf.set_value_BC(pores=pn.pores("right"), values=P_OUT)
+        sf.settings["cache"] = False
+        solver = b2.B200PCG(tol=RTOL, precond=precond)
+        sf.run(solver=solver)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            sf.run(solver=solver)
+            q = sf.rate(pores=pn.pores("left"))[0]
+        torch.cuda.synchronize()
+        out[precond] = {"time_s": (time.perf_counter() - t0) / steps,
+                        "iters": int(sf.soln.cg_iters), "rate_inlet": float(q)}
+        solver.ctx.close()
+    return out
+
+
 def gpu_arm(args):
     import torch
     import openpnm_b200 as b2
     from openpnm_b200 import dist as bdist
-    from openpnm_b200.device import pinned_copy
+    from openpnm_b200.device import Context, pinned_copy
 
     rank, world, local = bdist.init_process_group()
     if world != args.gpus:
@@ -252,23 +300,26 @@ def gpu_arm(args):
     rb, re = ranges[rank]
     x0p, x1p = rb // (n * n), re // (n * n)
 
-    # ---- host inputs (outside every timed region)
+    # ---- host inputs (outside every timed region): the network as the API user holds
+    # it (lazy lattice: no rank materialises the full throat list unless it needs it),
+    # the full conductance array, the BC array
     t_host = time.perf_counter()
+    pn = b2.Cubic(shape, spacing=1e-4, coords=False, lazy=world > 1)
+    g_full = pinned_copy(conductance(Nt))
     if world == 1:
-        pn = b2.Cubic(shape, spacing=1e-4, coords=False)
-        conns_h = pn.conns
-        g_h = conductance(Nt)
-        left, right = pn.pores("left"), pn.pores("right")
+        conns_h, g_h = pn.conns, g_full
     else:
         ids, conns_h = bdist.cubic_slab_throats(shape, x0p, x1p)
-        g_h = conductance(Nt, ids)
+        g_h = g_full[ids]
         del ids
-        left = np.arange(0, n * n, dtype=np.int64)
-        right = np.arange(Np - n * n, Np, dtype=np.int64)
+    left = np.arange(0, n * n, dtype=np.int64)
+    right = np.arange(Np - n * n, Np, dtype=np.int64)
     bcv_h = np.full(Np, np.nan)
     bcv_h[left] = P_IN
     bcv_h[right] = P_OUT
-    conns_h, g_h, bcv_h = pinned_copy(conns_h), pinned_copy(g_h), pinned_copy(bcv_h)
+    conns_h, bcv_h = pinned_copy(conns_h), pinned_copy(bcv_h)
+    if world > 1:
+        g_h = pinned_copy(g_h)
     t_host = time.perf_counter() - t_host
 
     ss = bdist.SlabSolver(Np, rb, re, device=local, fmt=args.fmt)
@@ -284,10 +335,39 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def device_step():
+    def allmax(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device=ctx.tdev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(vs):
+        t = torch.tensor([float(v) for v in vs], dtype=torch.float64, device=ctx.tdev)
+        if world > 1:
+            dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    def device_step(rtol=RTOL):
         f, nnz0, nnz = ss.assemble(conns_d, g_d, bcv_d, None)
-        x, it, rel, info = ss.solve(rtol=RTOL)
+        x, it, rel, info = ss.solve(rtol=rtol)
         return x, it, rel, info, nnz
+
+    def timed(fn, reps):
+        """max over ranks of the CUDA-event time of `reps` calls, per call [ms]"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ctx.stream):
+            e0.record()
+            for _ in range(reps):
+                out = fn()
+            e1.record()
+        barrier()
+        return allmax(e0.elapsed_time(e1)) / reps, out
+
+    def rates(x_loc):
+        xg = ss.gather(x_loc)
+        q = allsum([ss.rate(xg, left_d), ss.rate(xg, right_d)])
+        return q[0], q[1], xg
 
     if world > 1 and not args.no_p2p:
         ss.assemble(conns_d, g_d, bcv_d, None)
@@ -308,26 +388,16 @@ def gpu_arm(args):
             t_solve_ms.append(ctx.stats()["t_solve_ms"])
         ev1.record()
     barrier()
-    ms_total = ev0.elapsed_time(ev1)
     launches = ctx.stats()["kernel_launches"] - launches0
     clk = clocks.stop() if clocks else None
-    tmax = torch.tensor([ms_total], dtype=torch.float64, device=ctx.tdev)
-    nnz_t = torch.tensor([float(nnz)], dtype=torch.float64, device=ctx.tdev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(nnz_t)
-    ms_step = float(tmax.item()) / args.steps
-    nnz_global = int(nnz_t.item())
+    ms_step = allmax(ev0.elapsed_time(ev1)) / args.steps
+    nnz_global = int(allsum([nnz])[0])
     cg_iters = int(np.mean(iters))
     value = Np * cg_iters / (ms_step * 1e-3)
 
-    # ---- parity-side checks on the timed result: residual + conservation
-    xg = ss.gather(x)
-    q_in = torch.tensor([ss.rate(xg, left_d), ss.rate(xg, right_d)], dtype=torch.float64,
-                        device=ctx.tdev)
-    if world > 1:
-        dist.all_reduce(q_in)
-    q_in, q_out = float(q_in[0]), float(q_in[1])
+    # ---- parity-side checks on the timed result: conservation
+    q_in, q_out, _xg = rates(x)
+    del _xg
 
     # ---- dominant-kernel timing (live, CUDA events on the launching stream)
     fmt_code, nd = ctx.pcg_format()
@@ -344,144 +414,208 @@ def gpu_arm(args):
         fmt_spmv = 12 * (nnz_loc - n_loc) + 4 * n_loc + 24 * n_loc
     fmt_iter = fmt_spmv + 56 * n_loc          # K_BC: read x,r,p,Ap, write x,r,p
     peak, peak_src = peaks()
-    traffic = None
-    try:     # DRAM bytes per launch from the committed ncu capture of this very configuration
-        if world == 1 and n == 400 and fmt_code == 2:
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                tk = json.load(f)["cubic400_1gpu_dia"]["k_dia_spmv_dot"]
-            traffic = tk["dram_read_bytes"] + tk["dram_write_bytes"]
+    traffic, traffic_src = None, None
+    try:     # DRAM bytes per launch from the committed `ncu --set full` capture of K_A
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tk = json.load(f)["cubic400_1gpu_dia"]["k_dia_spmv_dot"]
+        per_row = (tk["dram_read_bytes"] + tk["dram_write_bytes"]) / 400 ** 3
+        if fmt_code == 2 and nd == 3:
+            traffic = per_row * n_loc
+            traffic_src = ("ncu --set full capture of this kernel at Cubic 400^3 on 1 GPU "
+                           "(profiles/r01_ncu_full_kA_kBC_v2.csv)" if world == 1 and n == 400 else
+                           f"{per_row:.1f} B/row from that capture x the {n_loc} rows of one launch "
+                           "here (ncu replays cannot run under torchrun)")
     except Exception:
         traffic = None
     ms_iter = float(np.mean(t_solve_ms)) / max(cg_iters, 1)
 
-    # ---- the same step with the multigrid preconditioner (1 GPU): assemble, build
-    # the hierarchy, solve to the same rtol -- time-to-solve is the metric here,
-    # an AMG iteration is not comparable to a PCG iteration
+    # ---- the same step with the multigrid preconditioner, at every N: assemble, build
+    # the hierarchy, solve to the same rtol -- time-to-solve is the metric here, an AMG
+    # iteration is not comparable to a PCG iteration
     amg = None
     if not args.no_amg:
         ctx.set_precond("amg")
         try:
             device_step()                               # warm-up (allocates the hierarchy)
-            barrier()
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(ctx.stream):
-                a0.record()
-                for _ in range(args.steps):
-                    xa, ita, rela, infoa, _nnz = device_step()
-                    sta = ctx.stats()
-                a1.record()
-            barrier()
-            t_amg = torch.tensor([a0.elapsed_time(a1) / args.steps], dtype=torch.float64,
-                                 device=ctx.tdev)
-            if world > 1:
-                dist.all_reduce(t_amg, op=dist.ReduceOp.MAX)
-            ms_amg = float(t_amg.item())
-            dx = float((xa - x).abs().max() / x.abs().max())
+            l0 = ctx.stats()["kernel_launches"]
+            ms_amg, (xa, ita, rela, infoa, _nnz) = timed(device_step, args.steps)
+            l_amg = (ctx.stats()["kernel_launches"] - l0) // args.steps
+            sta = ctx.stats()
+            dx = allmax(float((xa - x).abs().max())) / allmax(float(x.abs().max()))
+            qa_in, qa_out, _xg = rates(xa)
+            del _xg
+            nlev = len(ctx.amg_setup())
+            lv = [ctx.amg_level_info(l) for l in range(nlev)]
             amg = {"time_to_solve_s": ms_amg * 1e-3, "iters": int(ita), "relres": rela,
                    "info": int(infoa), "hierarchy_setup_ms": sta["t_setup_ms"],
-                   "solve_ms": sta["t_solve_ms"],
-                   "levels": ctx.amg_setup(),
+                   "solve_ms": sta["t_solve_ms"], "gpu_launches_per_step": int(l_amg),
+                   "levels": [[i["n_global"], "rows" if i["partitioned"] else "full"] for i in lv],
                    "max_rel_diff_vs_jacobi_pcg": dx,
+                   "rate_inlet": qa_in, "rate_outlet": qa_out,
                    "speedup_vs_jacobi_pcg": ms_step / ms_amg,
                    "what": "B200PCG(precond='amg'): aggregation-AMG K-cycle + flexible CG "
                            "(csrc/amg.cu); step = assembly + hierarchy build + solve"
-                           + ("" if world == 1 else "; slabs: one hierarchy, levels row-partitioned "
-                              "by the slabs, small levels replicated")}
+                           + ("" if world == 1 else "; slabs: ONE hierarchy, levels marked 'rows' "
+                              "are row-partitioned by the slabs, 'full' ones replicated")}
             del xa
         finally:
             ctx.set_precond("jacobi")
-            ss.assemble(conns_d, g_d, bcv_d, None)
 
-    # ---- e2e through the public API with HOST buffers: every step copies its
-    # inputs from pinned host memory and reads the solution back
-    e2e = None
+    # ---- parity at this size (north star: x and rate within 1e-8 at CG rtol 1e-12):
+    # the two independent solvers at rtol 1e-12 and 1e-13 against each other, residuals on
+    # the canonical CSR (b200_spmv(B200_MAT_SYSTEM)), and -- for N > 1 -- against a
+    # single-GPU solve of the whole problem made by rank 0 in a context of its own
+    parity = None
+    if not args.no_parity:
+        parity = {"what": "max |x_a - x_b| / max |x_b| and relative inlet-rate differences between "
+                          "Jacobi-PCG and multigrid-FCG solves of this very system; residual = "
+                          "|b - A x|_2/|b|_2 on the canonical CSR", "runs": []}
+        sols = {}
+        b_loc = ctx.get_b()
+        bn2 = allsum([float((b_loc * b_loc).sum())])[0]
+        for rtol in (1e-12, 1e-13):
+            for precond in (("jacobi", "amg") if not args.no_amg else ("jacobi",)):
+                ctx.set_precond(precond)
+                ms_p, (xp, itp, relp, infop, _nnz) = timed(lambda: device_step(rtol), 1)
+                qi, qo, xg = rates(xp)
+                r = ctx.spmv(1, xg) - ctx.get_b()
+                res = (allsum([float((r * r).sum())])[0] / bn2) ** 0.5
+                del r, xg
+                sols[(rtol, precond)] = (xp.clone(), qi, qo)
+                parity["runs"].append({"rtol": rtol, "precond": precond, "iters": int(itp),
+                                       "info": int(infop), "time_to_solve_s": ms_p * 1e-3,
+                                       "residual_canonical_csr": res, "rate_inlet": qi,
+                                       "rate_outlet": qo,
+                                       "conservation": abs(qi + qo) / abs(qi) if qi else None})
+        ctx.set_precond("jacobi")
+
+        def diff(a, b):
+            xa_, qa_, _ = sols[a]
+            xb_, qb_, _ = sols[b]
+            return {"x": allmax(float((xa_ - xb_).abs().max())) / allmax(float(xb_.abs().max())),
+                    "rate_inlet": abs(qa_ - qb_) / abs(qb_)}
+        pairs = {}
+        if not args.no_amg:
+            pairs["amg_vs_jacobi@1e-12"] = diff((1e-12, "amg"), (1e-12, "jacobi"))
+            pairs["amg_vs_jacobi@1e-13"] = diff((1e-13, "amg"), (1e-13, "jacobi"))
+            pairs["amg@1e-12_vs_amg@1e-13"] = diff((1e-12, "amg"), (1e-13, "amg"))
+        pairs["jacobi@1e-12_vs_jacobi@1e-13"] = diff((1e-12, "jacobi"), (1e-13, "jacobi"))
+        # the benchmarked tolerance against the tight solve: what rtol 1e-10 really delivers
+        sols[(RTOL, "jacobi")] = (x, q_in, q_out)
+        pairs["jacobi@1e-10_vs_jacobi@1e-13"] = diff((RTOL, "jacobi"), (1e-13, "jacobi"))
+        if world > 1 and not args.no_cross_check:
+            # rank 0 alone solves the whole problem on its GPU (multigrid, rtol 1e-13) and
+            # compares the gathered slab solution with it: N GPUs against 1 GPU in one run
+            ref_key = (1e-13, "amg") if not args.no_amg else (1e-13, "jacobi")
+            xg = ss.gather(sols[ref_key][0])
+            cross = None
+            if rank == 0:
+                ctx1 = Context(local)
+                ctx1.set_precond("amg" if not args.no_amg else "jacobi")
+                ctx1.build_laplacian(pn.conns, g_full, Np)
+                ctx1.apply_bcs(bcv_h, None)
+                x1, it1, rel1, info1 = ctx1.pcg(rtol=1e-13)
+                q1 = float(ctx1.rate_pores(x1, left).sum().item())
+                cross = {"x": float((xg - x1).abs().max() / x1.abs().max()),
+                         "rate_inlet": abs(sols[ref_key][1] - q1) / abs(q1),
+                         "single_gpu_iters": int(it1), "single_gpu_info": int(info1)}
+                del x1
+                ctx1.close()
+            del xg
+            barrier()
+            if cross is not None:
+                pairs[f"{world}_gpus_vs_1_gpu@1e-13"] = cross
+        parity["pairs"] = pairs
+        if rank == 0:
+            tight = {k: v for k, v in pairs.items() if "1e-10" not in k}
+            parity["max_pairwise_x_at_rtol<=1e-12"] = max(v["x"] for v in tight.values())
+            parity["max_pairwise_rate_at_rtol<=1e-12"] = max(v["rate_inlet"] for v in tight.values())
+            parity["within_1e-8"] = bool(parity["max_pairwise_x_at_rtol<=1e-12"] <= 1e-8 and
+                                         parity["max_pairwise_rate_at_rtol<=1e-12"] <= 1e-8)
+        sols.clear()
+
+    # ---- e2e through the public API with HOST buffers: every step copies its inputs
+    # from pinned host memory, checks the topology on the device, solves and reads the
+    # solution + the inlet rate back.  The same call on 1 GPU and under torchrun.
+    ph = b2.Phase(pn)
+    dict.__setitem__(ph, "throat.hydraulic_conductance", g_full)      # the pinned buffer
+    sf = b2.StokesFlow(network=pn, phase=ph)
     if world == 1:
-        ph = b2.Phase(pn)
-        dict.__setitem__(ph, "throat.hydraulic_conductance", g_h)      # the pinned buffers
-        sf = b2.StokesFlow(network=pn, phase=ph)
         dict.__setitem__(pn, "throat.conns", conns_h)
-        dict.__setitem__(sf, "pore.bc.value", bcv_h)
-        dict.__setitem__(sf, "pore.bc.rate", pinned_copy(np.full(Np, np.nan)))
-        sf.settings["validate_topology"] = False    # reference's check is O(minutes) at 64M pores
-        sf.settings["cache"] = False                # re-upload + re-assemble every step
-        solver = b2.B200PCG(tol=RTOL, fmt=args.fmt)
-        solver._ctx = ctx
+    dict.__setitem__(sf, "pore.bc.value", bcv_h)
+    dict.__setitem__(sf, "pore.bc.rate", pinned_copy(np.full(Np, np.nan)))
+    sf.settings["cache"] = False                # re-upload + re-assemble every step
+
+    def e2e_leg(precond):
+        solver = b2.B200PCG(tol=RTOL, fmt=args.fmt, precond=precond, device=local)
+        if world == 1:
+            solver._ctx = ctx
+            ctx.set_precond(precond)
+        else:
+            solver._slab, solver._slab_p2p = ss, (p2p if precond == "jacobi" else False)
+            solver._slab_key = (id(pn), world, rank, solver.device, solver.fmt)
         sf.run(solver=solver)                        # warm-up
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
-        e2e_iters = []
-        for _ in range(args.steps):
+        its_ = []
+        reps = min(args.steps, 5)                    # host-buffer legs: a few steps suffice
+        for _ in range(reps):
             sf.run(solver=solver)
             qq = sf.rate(pores=left)[0]
-            e2e_iters.append(sf.soln.cg_iters)
-        torch.cuda.synchronize()
-        t_e2e = (time.perf_counter() - t0) / args.steps
-        e2e = {"value": Np * float(np.mean(e2e_iters)) / t_e2e, "unit": "DOF*iter/s",
-               "h2d_bytes_per_step": int(conns_h.nbytes + g_h.nbytes + 2 * bcv_h.nbytes),
-               "d2h_bytes_per_step": int(8 * Np + 8 * left.size),
-               "ms_per_step": 1e3 * t_e2e, "api": "openpnm_b200.StokesFlow.run + rate",
-               "rate_inlet": float(qq)}
-        if amg is not None:
-            # the same public call with the multigrid preconditioner (host buffers in and out)
-            ctx.set_precond("amg")
-            try:
-                sf.run(solver=solver)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for _ in range(args.steps):
-                    sf.run(solver=solver)
-                    qa = sf.rate(pores=left)[0]
-                torch.cuda.synchronize()
-                amg["e2e_time_to_solve_s"] = (time.perf_counter() - t0) / args.steps
-                amg["e2e_rate_inlet"] = float(qa)
-            finally:
-                ctx.set_precond("jacobi")
-    else:
-        # slab API (openpnm_b200.dist.SlabSolver): each rank uploads the throats of its
-        # slab + the BC array, assembles, solves and downloads its part of x
-        x_h = pinned_copy(np.zeros(re - rb))
-
-        def e2e_step():
-            ss.assemble(conns_h, g_h, bcv_h, None)
-            xl, it_, rel_, info_ = ss.solve(rtol=RTOL)
-            with torch.cuda.stream(ctx.stream):
-                torch.from_numpy(x_h).copy_(xl, non_blocking=True)
-            ctx.synchronize()
-            return it_
-
-        e2e_step()
+            its_.append(sf.soln.cg_iters)
         barrier()
-        t0 = time.perf_counter()
-        e2e_iters = [e2e_step() for _ in range(args.steps)]
-        barrier()
-        t_e2e = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64,
-                             device=ctx.tdev)
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        t_e2e = float(t_e2e.item())
-        nbytes = torch.tensor([float(conns_h.nbytes + g_h.nbytes + bcv_h.nbytes),
-                               float(x_h.nbytes)], dtype=torch.float64, device=ctx.tdev)
-        dist.all_reduce(nbytes)
-        e2e = {"value": Np * float(np.mean(e2e_iters)) / t_e2e, "unit": "DOF*iter/s",
-               "h2d_bytes_per_step": int(nbytes[0].item()),
-               "d2h_bytes_per_step": int(nbytes[1].item()), "ms_per_step": 1e3 * t_e2e,
-               "api": "openpnm_b200.dist.SlabSolver.assemble + solve, x to host (all ranks)"}
+        return allmax((time.perf_counter() - t0) / reps), float(np.mean(its_)), float(qq)
+
+    t_e2e, it_e2e, qq = e2e_leg("jacobi")
+    h2d = conns_h.nbytes + g_h.nbytes + 2 * bcv_h.nbytes    # per rank: its throats + the BC arrays
+    if world > 1:
+        h2d = int(allsum([h2d])[0])
+    e2e = {"value": Np * it_e2e / t_e2e, "unit": "DOF*iter/s",
+           "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(world * (8 * Np + 8 * left.size)),
+           "ms_per_step": 1e3 * t_e2e, "time_to_solve_s": t_e2e,
+           "api": "openpnm_b200.StokesFlow.run(solver=B200PCG()) + rate()"
+                  + ("" if world == 1 else " under torchrun (every rank: its slab's inputs up, "
+                     "the full x down)"),
+           "validate_topology": bool(sf.settings["validate_topology"]),
+           "rate_inlet": qq}
+    if amg is not None:
+        ta, ia, qa = e2e_leg("amg")
+        amg["e2e_time_to_solve_s"] = ta
+        amg["e2e_rate_inlet"] = qa
+        amg["e2e_iters"] = ia
+        ctx.set_precond("jacobi")
 
     cpu = None
+    matched = None
     if rank == 0 and world == 1 and not args.no_cpu:
         r = reference_openpnm_sample(args.ref_size)
         if r is not None:
             cpu = {"value": r["Np"] * r["iters"] / r["t_step"], "unit": "DOF*iter/s", "cores": 1,
-                   "kind": "reference",
+                   "kind": "reference", "time_to_solve_s": r["t_step"], "iters": r["iters"],
+                   "rate_inlet": r["rate"],
                    "sample": f"unmodified OpenPNM StokesFlow.run(solver=ScipyCG(tol={RTOL:g})) + "
                              f"rate() on Cubic {args.ref_size}^3, same distribution/BCs: "
-                             f"{r['iters']} iterations, {r['t_step']:.1f} s; SciPy CG is serial"}
+                             f"{r['iters']} iterations, {r['t_step']:.1f} s; SciPy CG is serial. "
+                             + pardiso_note()}
         else:
             r = cpu_solve_sample(args.cpu_size)
             cpu = {"value": r["Np"] * r["iters"] / r["t_step"], "unit": "DOF*iter/s", "cores": 1,
-                   "kind": "port",
-                   "sample": f"Cubic {args.cpu_size}^3 same distribution/BCs/rtol, {r['iters']} "
-                             f"iterations, {r['t_step']:.1f} s (assembly {r['t_assemble']:.1f} s); "
-                             f"numpy assembly + SciPy CSR SpMV Jacobi-PCG, serial"}
+                   "kind": "port", "time_to_solve_s": r["t_step"], "iters": r["iters"],
+                   "rate_inlet": float(r["rate"]),
+                   "sample": f"oracle port on Cubic {args.cpu_size}^3 same distribution/BCs/rtol, "
+                             f"{r['iters']} iterations, {r['t_step']:.1f} s; numpy assembly + SciPy "
+                             f"CSR SpMV Jacobi-PCG, serial. " + pardiso_note()}
+        # the GPU arm on that very problem, through the same public call
+        size_m = args.ref_size if cpu["kind"] == "reference" else args.cpu_size
+        m = matched_leg(b2, size_m, max(args.steps, 3))
+        matched = {"workload": f"Cubic {size_m}^3 StokesFlow, the CPU arm's problem, through "
+                               "StokesFlow.run + rate from host arrays",
+                   "gpu": m, "cpu_time_s": cpu["time_to_solve_s"], "cpu_iters": cpu["iters"],
+                   "same_config_time_ratio": cpu["time_to_solve_s"] / m["jacobi"]["time_s"],
+                   "same_config_time_ratio_amg": cpu["time_to_solve_s"] / m["amg"]["time_s"],
+                   "rate_inlet_rel_diff_vs_cpu":
+                       abs(m["jacobi"]["rate_inlet"] - cpu["rate_inlet"]) / abs(cpu["rate_inlet"])}
 
     if rank == 0:
         line = {
@@ -505,6 +639,7 @@ def gpu_arm(args):
                          "k_csr_stream_spmv_dot)", "achieved": b_spmv / (t_ka * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s",
                          "frac": b_spmv / (t_ka * 1e-3) / 1e9 / peak, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "peak_source": peak_src, "ms": t_ka,
                          "algorithmic_bytes": int(b_spmv), "format_bytes": int(fmt_spmv),
                          "frac_format_bytes": fmt_spmv / (t_ka * 1e-3) / 1e9 / peak},
@@ -517,10 +652,13 @@ def gpu_arm(args):
         }
         if amg:
             line["amg"] = amg
-        if e2e:
-            line["e2e"] = e2e
+        if parity:
+            line["parity"] = parity
+        line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        if matched:
+            line["matched"] = matched
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -541,6 +679,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-p2p", action="store_true")
     ap.add_argument("--no-amg", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-cross-check", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

@@ -38,6 +38,30 @@ _SRC_KINDS = {
 }
 
 
+_COPY_POOL = None
+
+
+def _host_copy(src, min_chunk=1 << 21):
+    """A fresh array with the contents of `src` (the page-locked staging buffer is
+    reused by the next run, the caller keeps the result): large arrays are copied by a
+    few threads -- numpy releases the GIL inside copyto -- because one core moves only
+    ~5 GB/s (0.11 s for the 64 M doubles of a 400^3 solution)."""
+    global _COPY_POOL
+    n = src.size
+    dst = np.empty_like(src)
+    parts = min(8, n // min_chunk)
+    if parts < 2:
+        np.copyto(dst, src)
+        return dst
+    if _COPY_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _COPY_POOL = ThreadPoolExecutor(max_workers=8)
+    edges = np.linspace(0, n, parts + 1).astype(np.int64)
+    list(_COPY_POOL.map(lambda k: np.copyto(dst[edges[k]:edges[k + 1]], src[edges[k]:edges[k + 1]]),
+                        range(parts)))
+    return dst
+
+
 class SolutionContainer(dict):
     """openpnm/algorithms/_solution.py:10"""
     pass
@@ -413,8 +437,9 @@ class Transport(dict):
         self._update_hook(None)        # raises if a model needs the host (single-GPU only)
         try:
             srcs = self._sources()
-            f, nnz0, nnz = ss.assemble(conns_dev, g[sel], self["pore.bc.value"],
-                                       self["pore.bc.rate"], keep_zero_diag=len(srcs) > 0)
+            f, nnz0, nnz = ss.assemble(conns_dev, self._slab_take(ctx, g, sel),
+                                       self["pore.bc.value"], self["pore.bc.rate"],
+                                       keep_zero_diag=len(srcs) > 0)
             ctx.clear_sources()
             if solver._slab_p2p is None:              # maps the peers once (source-free operator)
                 solver._slab_p2p = ss.enable_p2p()
@@ -436,7 +461,7 @@ class Transport(dict):
             raise
         x_dev = ss.gather(x_loc)
         self._x_dev = x_dev
-        x = x_dev.cpu().numpy()
+        x = self._download(ctx, x_dev)
         q = self.settings["quantity"]
         dict.__setitem__(self, q, x)
         self.soln[q] = SteadyStateSolution(x)
@@ -472,7 +497,8 @@ class Transport(dict):
             not getattr(net, "_conns_touched", False)
         if analytic:
             band = ny * nz if nx > 1 else (nz if ny > 1 else 1)
-            sel, conns_loc = bdist.cubic_slab_throats(shape, rb // (ny * nz), re // (ny * nz))
+            _, conns_loc = bdist.cubic_slab_throats(shape, rb // (ny * nz), re // (ny * nz))
+            sel = bdist.cubic_slab_throat_ranges(shape, rb // (ny * nz), re // (ny * nz))
         else:
             conns = np.asarray(net["throat.conns"], dtype=np.int64)
             band = bdist.bandwidth(conns)
@@ -486,6 +512,23 @@ class Transport(dict):
         self._slab_plan_cache = (key, out)
         return out
 
+    def _slab_take(self, ctx, a, sel):
+        """Per-throat array of this rank's throats on the device: `sel` is either an
+        index array or (lattice) a list of contiguous (begin, end) ranges, which are
+        sliced into a page-locked staging buffer and uploaded from there."""
+        import torch
+        if not isinstance(sel, list):
+            return a[sel]
+        n = sum(e - b for b, e in sel)
+        stage = getattr(self, "_g_stage", None)
+        if stage is None or stage.numel() != n:
+            stage = self._g_stage = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        out, o = stage.numpy(), 0
+        for b, e in sel:
+            out[o:o + e - b] = a[b:e]
+            o += e - b
+        return ctx.to_device(stage, torch.float64)
+
     def _download(self, ctx, x_dev):
         """Device -> host through a page-locked staging buffer (kept per size)."""
         import torch
@@ -497,7 +540,7 @@ class Transport(dict):
         with torch.cuda.stream(ctx.stream):
             stage.copy_(x_dev, non_blocking=True)
         ctx.synchronize()
-        return stage.numpy().copy()
+        return _host_copy(stage.numpy())
 
     @property
     def A(self):

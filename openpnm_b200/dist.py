@@ -21,6 +21,7 @@ import os
 import numpy as np
 
 __all__ = ["slab_ranges", "cubic_slab_ranges", "slab_throat_mask", "cubic_slab_throats",
+           "cubic_slab_throat_ranges",
            "bandwidth", "coordinate_order", "SlabSolver", "init_process_group",
            "slab_topology_check", "join_slab_clusters"]
 
@@ -98,6 +99,23 @@ def cubic_slab_throats(shape, x0, x1):
         conns[:, 0] = np.concatenate(tails)
         conns[:, 1] = np.concatenate(heads)
     return ids, conns
+
+
+def cubic_slab_throat_ranges(shape, x0, x1):
+    """The same throats as `cubic_slab_throats` as three contiguous id ranges
+    [(begin, end)] (z-, y-, x-throats of the planes): per-throat arrays of a slab are
+    three slices of the global arrays, not a gather."""
+    nx, ny, nz = (int(s) for s in shape)
+    out = []
+    if nz > 1:
+        out.append((x0 * ny * (nz - 1), x1 * ny * (nz - 1)))
+    off = nx * ny * (nz - 1)
+    if ny > 1:
+        out.append((off + x0 * (ny - 1) * nz, off + x1 * (ny - 1) * nz))
+    off += nx * (ny - 1) * nz
+    if nx > 1:
+        out.append((off + max(x0 - 1, 0) * ny * nz, off + min(x1, nx - 1) * ny * nz))
+    return out
 
 
 def bandwidth(conns):

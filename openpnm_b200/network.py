@@ -129,13 +129,33 @@ class Cubic(Network):
     labels left/right (x), front/back (y), bottom/top (z) and the xmin/xmax...
     aliases (_skgraph/generators/tools/_funcs.py:216-250)."""
 
-    def __init__(self, shape, spacing=1.0, coords=True):
+    def __init__(self, shape, spacing=1.0, coords=True, lazy=False):
+        """lazy=True keeps only the shape: 'throat.conns' (and 'throat.all') are generated
+        when first read.  A slab-parallel run never reads them -- every rank derives the
+        throats of its own planes from index arithmetic (openpnm_b200.dist) -- so a 400^3
+        lattice costs no rank the 3 GB of the full list."""
         shape = np.array(shape, ndmin=1, dtype=int)
         if shape.size < 3:
             shape = np.concatenate((shape, np.ones(3 - shape.size, dtype=int)))
         nx, ny, nz = (int(s) for s in shape)
         n = nx * ny * nz
-        idx = np.arange(n, dtype=np.int64).reshape(nx, ny, nz)
+        self.shape = (nx, ny, nz)
+        self.spacing = np.ones(3) * np.asarray(spacing, dtype=float)
+        if lazy:
+            _Store.__init__(self)
+            self._Np = n
+            self._Nt = (nx - 1) * ny * nz + nx * (ny - 1) * nz + nx * ny * (nz - 1)
+            dict.__setitem__(self, "pore.all", np.ones(n, dtype=bool))
+        else:
+            super().__init__(coords=None, conns=self._lattice_conns(), Np=n)
+        if coords:
+            ii, jj, kk = np.unravel_index(np.arange(n), (nx, ny, nz))
+            c = (np.vstack((ii, jj, kk)).T + 0.5) * self.spacing
+            dict.__setitem__(self, "pore.coords", c)
+
+    def _lattice_conns(self):
+        nx, ny, nz = self.shape
+        idx = np.arange(nx * ny * nz, dtype=np.int64).reshape(nx, ny, nz)
         tails = np.concatenate((idx[:, :, :-1].ravel(), idx[:, :-1, :].ravel(),
                                 idx[:-1, :, :].ravel()))
         heads = np.concatenate((idx[:, :, 1:].ravel(), idx[:, 1:, :].ravel(),
@@ -143,14 +163,22 @@ class Cubic(Network):
         conns = np.empty((tails.size, 2), dtype=np.int64)
         conns[:, 0] = tails
         conns[:, 1] = heads
-        del tails, heads, idx
-        super().__init__(coords=None, conns=conns, Np=n)
-        self.shape = (nx, ny, nz)
-        self.spacing = np.ones(3) * np.asarray(spacing, dtype=float)
-        if coords:
-            ii, jj, kk = np.unravel_index(np.arange(n), (nx, ny, nz))
-            c = (np.vstack((ii, jj, kk)).T + 0.5) * self.spacing
-            dict.__setitem__(self, "pore.coords", c)
+        return conns
+
+    def __missing__(self, key):
+        # lazy lattice: materialise the throat arrays on first use
+        if key == "throat.conns":
+            dict.__setitem__(self, key, self._lattice_conns())
+            return dict.__getitem__(self, key)
+        if key == "throat.all":
+            dict.__setitem__(self, key, np.ones(self._Nt, dtype=bool))
+            return dict.__getitem__(self, key)
+        raise KeyError(key)
+
+    def __setitem__(self, key, value):
+        if key == "throat.conns":
+            self._conns_touched = True        # no longer the generator's lattice
+        super().__setitem__(key, value)
 
     def _face(self, axis, last):
         """Sorted pore indices of one face, from index arithmetic (no Np-long temporaries)."""

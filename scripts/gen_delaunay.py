@@ -4,7 +4,7 @@ ordering by coordinate"), edges from `scipy.spatial.Delaunay(...).vertex_neighbo
 (upper triangle; the same edge set as the reference's `tri_to_am`,
 openpnm/_skgraph/tools/_funcs.py:646-669, without its Python loop).
 
-    python scripts/gen_delaunay.py N [seed] -> data/delaunay_<N>.npz  (conns int32, coords f32)
+    python scripts/gen_delaunay.py N [seed] -> $B200_DATA_DIR/delaunay_<N>.npz (default /tmp/b200_data)  (conns int32, coords f32)
 
 The 10 M-pore file (~0.75 GB) is git-ignored; it travels to the GPU box with the
 snapshot for the config-4 runs and is deleted afterwards."""
@@ -39,7 +39,7 @@ if __name__ == "__main__":
     N = int(sys.argv[1])
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     conns, coords = generate(N, seed)
-    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data",
+    out = os.path.join(os.environ.get("B200_DATA_DIR", "/tmp/b200_data"),
                        f"delaunay_{N}.npz")
     np.savez(out, conns=conns, coords=coords)
     print("wrote", out, os.path.getsize(out) / 1e6, "MB")

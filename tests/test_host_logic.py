@@ -178,3 +178,22 @@ def test_b200pcg_precond_option():
     assert b2.B200PCG(precond="amg").precond == "amg"
     with pytest.raises(ValueError):
         b2.B200PCG(precond="ilu")
+
+
+def test_cubic_slab_throat_ranges_are_the_slab_throat_ids():
+    """the three contiguous id ranges of a lattice slab == the ids of cubic_slab_throats;
+    the lazy Cubic materialises the same conns as the eager one"""
+    from openpnm_b200 import dist as bdist
+    from openpnm_b200.network import Cubic
+    for shape in [(8, 5, 6), (13, 4, 7), (5, 1, 4), (6, 3, 1)]:
+        pl = shape[1] * shape[2]
+        for world in (1, 2, 3):
+            for rb, re in bdist.cubic_slab_ranges(shape, world):
+                ids, _ = bdist.cubic_slab_throats(shape, rb // pl, re // pl)
+                rg = bdist.cubic_slab_throat_ranges(shape, rb // pl, re // pl)
+                ids2 = np.concatenate([np.arange(a, b) for a, b in rg]) if rg else np.zeros(0, int)
+                assert np.array_equal(ids, ids2)
+        eager, lazy = Cubic(shape, coords=False), Cubic(shape, coords=False, lazy=True)
+        assert "throat.conns" not in lazy.keys() and lazy.Nt == eager.Nt
+        assert np.array_equal(lazy.pores("right"), eager.pores("right"))
+        assert np.array_equal(lazy.conns, eager.conns)
