@@ -263,6 +263,34 @@ int b200_picard_cb(b200_ctx* ctx, const double* x0, double relaxation,
                    int64_t* num_iter, int* converged, int64_t* cg_iters_total,
                    int* last_info, b200_update_fn update, void* user);
 
+/* ------------------- conductance that follows the quantity, on the device (f-3)
+ * For the usual chain  X -> pore property P(X) = sum_k poly[k] X^k
+ * (models/misc polynomial) -> throat value (given array; or mean / min / max of
+ * the two pore values, models/misc from_neighbor_pores: interp 0 / 1 / 2) ->
+ * conduit conductance
+ *   B200_COND_HYDRAULIC  generic_hydraulic, g_i = F_i / mu_i in series
+ *                        (models/physics/hydraulic_conductance/_funcs.py:37-53)
+ *   B200_COND_POISSON    _poisson_conductance, g_i = D_i F_i in series
+ *                        (models/physics/_utils.py:46-61; generic_diffusive,
+ *                        generic_thermal, generic_electrical)
+ * with size factors (Nt,3) row-major (sf_cols = 3) or (Nt,) (sf_cols = 1).
+ * While a model is set, b200_picard re-evaluates g at the current iterate,
+ * re-assembles (K1) and re-applies the BCs (K2, the arrays given here) before
+ * every linearisation: `_update_iterative_props` + `_update_A_and_b`
+ * (_algorithm.py:69-91, _reactive_transport.py:226-232) without leaving the
+ * device.  All arrays are caller-owned device memory and must outlive the
+ * model; poly_h is host.  Single GPU.                                        */
+enum { B200_COND_HYDRAULIC = 0, B200_COND_POISSON = 1 };
+int b200_set_conductance_model(b200_ctx* ctx, int kind, const int64_t* conns,
+                               int64_t Nt, int64_t Np, const double* poly_h,
+                               int npoly, int interp, const double* throat_prop,
+                               const double* size_factors, int sf_cols,
+                               const double* bc_value, const double* bc_rate,
+                               int keep_zero_diag);
+int b200_clear_conductance_model(b200_ctx* ctx);
+int b200_update_conductance(b200_ctx* ctx, const double* x);
+int b200_conductance_values(b200_ctx* ctx, double* g_out);
+
 /* ------------------------------------------------ transient (explicit RK45)
  * Replaces TransientReactiveTransport.run + _build_rhs
  * (openpnm/algorithms/_transient_reactive_transport.py:51-123) with
@@ -307,6 +335,10 @@ int b200_get_stats(b200_ctx* ctx, b200_stats* out);
  * on the scaled operator, 1 = K_B x/r update + norms, 2 = K_C p update,
  * 3 = K3 plain CSR SpMV of the system matrix.                                */
 int b200_time_kernel(b200_ctx* ctx, int which, int reps, double* ms_avg);
+/* Bytes one K_A launch must move in the operator's storage format (DIA-sym: nd+3
+ * doubles per row; irregular: 12 B per stored entry of the sliced-ELL copy, padding
+ * included, + permutation + the three vectors) and the stored entries.          */
+int b200_operator_bytes(b200_ctx* ctx, int64_t* bytes, int64_t* entries);
 
 /* --------------------------------------------------- host-buffer entry points
  * What a ctypes binder holding numpy arrays calls; H2D/D2H copies inside.

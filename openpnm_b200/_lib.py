@@ -87,12 +87,18 @@ SIGNATURES = {
                               _pi64, _pint]),
     "b200_picard_cb": (C.c_int, [_p, _p, _dbl, _i64, _dbl, _dbl, _dbl, _i64, _p, _pi64, _pint,
                                  _pi64, _pint, _p, _p]),
+    "b200_set_conductance_model": (C.c_int, [_p, C.c_int, _p, _i64, _i64, _p, C.c_int, C.c_int, _p,
+                                             _p, C.c_int, _p, _p, C.c_int]),
+    "b200_clear_conductance_model": (C.c_int, [_p]),
+    "b200_update_conductance": (C.c_int, [_p, _p]),
+    "b200_conductance_values": (C.c_int, [_p, _p]),
     "b200_transient_rk45": (C.c_int, [_p, _p, _p, _dbl, _dbl, _dbl, _dbl, _p, _i64, _i64, _p, _p,
                                       _pi64, _pi64, _pi64, _pint]),
     "b200_rate_pores": (C.c_int, [_p, _p, _p, _i64, _p]),
     "b200_rate_throats": (C.c_int, [_p, _p, _p, _p, _p, _i64, _p]),
     "b200_get_stats": (C.c_int, [_p, C.POINTER(Stats)]),
     "b200_time_kernel": (C.c_int, [_p, C.c_int, C.c_int, _pdbl]),
+    "b200_operator_bytes": (C.c_int, [_p, _pi64, _pi64]),
     "b200_solve_coo_h": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _dbl, _dbl, _i64, _p,
                                    _pi64, _pdbl, _pint]),
     "b200_nccl_unique_id": (C.c_int, [_p]),

@@ -38,6 +38,22 @@ _SRC_KINDS = {
 }
 
 
+# conduit-conductance models with a device kernel: name -> (kind, argument names of the
+# pore property, the throat property and the size factors, their defaults)
+_COND_KINDS = {
+    "generic_hydraulic": ("hydraulic", ("pore_viscosity", "throat_viscosity", "size_factors"),
+                          ("pore.viscosity", "throat.viscosity", "throat.hydraulic_size_factors")),
+    "generic_diffusive": ("poisson", ("pore_diffusivity", "throat_diffusivity", "size_factors"),
+                          ("pore.diffusivity", "throat.diffusivity",
+                           "throat.diffusive_size_factors")),
+    "generic_thermal": ("poisson", ("pore_conductivity", "throat_conductivity", "size_factors"),
+                        ("pore.thermal_conductivity", "throat.thermal_conductivity",
+                         "throat.diffusive_size_factors")),
+    "generic_electrical": ("poisson", ("pore_conductivity", "throat_conductivity", "size_factors"),
+                           ("pore.electrical_conductivity", "throat.electrical_conductivity",
+                            "throat.diffusive_size_factors")),
+}
+
 _COPY_POOL = None
 
 
@@ -373,12 +389,23 @@ class Transport(dict):
                 cg_rtol=cg_rtol, cg_maxiter=0 if solver.maxiter is None else solver.maxiter,
                 update=self._update_hook(ctx))
         except _lib.B200Error as e:
+            if getattr(self, "_gplan", None) is not None:
+                self._gplan = None
+                ctx.clear_conductance_model()
             if e.code == -4:
                 raise Exception("A or b contains inf/nan values") from e
             raise
         self._x_dev = x_dev
         x = self._download(ctx, x_dev)
         q = self.settings["quantity"]
+        if getattr(self, "_gplan", None) is not None:
+            # leave the phase as regenerate_models would at the converged x
+            plan, self._gplan = self._gplan, None
+            try:
+                self._phase[self.settings["conductance"]] = ctx.conductance_values().cpu().numpy()
+                self._phase[plan["pore_prop"]] = sum(a * x ** k for k, a in enumerate(plan["poly"]))
+            finally:
+                ctx.clear_conductance_model()
         dict.__setitem__(self, q, x)
         self.soln[q] = SteadyStateSolution(x)      # a view, as in _solution.py:17-20
         self.soln.is_converged = bool(conv)
@@ -393,6 +420,63 @@ class Transport(dict):
 
     def _post_run(self, x):
         pass
+
+    def _phase_model(self, prop):
+        """(name, arguments) of the phase model that produces `prop`, or None"""
+        models = getattr(self._phase, "models", None) or {}
+        key = prop if prop in models else next((k for k in models if k.split("@")[0] == prop), None)
+        if key is None:
+            return None
+        m = models[key]
+        fn = m["model"]
+        return (fn if isinstance(fn, str) else getattr(fn, "__name__", str(fn))), m
+
+    def _device_conductance_plan(self, iterative):
+        """The chain quantity -> polynomial pore property -> (neighbour-interpolated or
+        fixed) throat property -> generic_hydraulic / generic_diffusive / ... conductance
+        has device kernels (b200_set_conductance_model); returns its description, or None
+        when the conductance follows the quantity through anything else (then the host
+        hook regenerates the models every iteration)."""
+        gkey, q = self.settings["conductance"], self.settings["quantity"]
+        gm = self._phase_model(gkey)
+        if gm is None or gm[0] not in _COND_KINDS:
+            return None
+        kind, names, defaults = _COND_KINDS[gm[0]]
+        pkey, tkey, skey = (gm[1].get(n, d) for n, d in zip(names, defaults))
+        pm = self._phase_model(pkey)
+        if pm is None or pm[0] != "polynomial" or pm[1].get("prop") != q:
+            return None
+        poly = np.asarray(pm[1].get("a"), dtype=np.float64).ravel()
+        if poly.size < 1 or poly.size > 8:
+            return None
+        tm, throat_prop, interp = self._phase_model(tkey), None, "mean"
+        if tm is None:
+            if tkey in iterative:
+                return None
+            throat_prop = np.asarray(self._phase[tkey], dtype=np.float64)
+        elif tm[0] == "from_neighbor_pores" and tm[1].get("prop") == pkey and \
+                tm[1].get("mode", "min") in ("mean", "min", "max"):
+            interp = tm[1].get("mode", "min")
+        else:
+            return None
+        if set(iterative) - {pkey, tkey, gkey} - self._device_source_props(iterative):
+            return None          # something else follows the quantity through Python
+        try:
+            sf = self.network[skey]
+        except KeyError:
+            return None
+        if isinstance(sf, dict):
+            return None
+        return dict(kind=kind, poly=poly, pore_prop=pkey, throat_prop_key=tkey,
+                    throat_prop=throat_prop, interp=interp, size_factors=np.asarray(sf))
+
+    def _device_source_props(self, iterative):
+        """iterative properties that are the outputs of device-evaluated source terms"""
+        out = set()
+        for it in self["pore.source"].keys():
+            if not self._source_on_host(it, iterative):
+                out |= {f"pore.{it}", f"pore.{it}.S1", f"pore.{it}.S2", f"pore.{it}.rate"}
+        return out
 
     def _update_hook(self, ctx):
         """Callback for b200_picard_cb, or None when everything that depends on
@@ -427,7 +511,16 @@ class Transport(dict):
         ctx = ss.ctx
         ctx.set_precond(getattr(solver, "precond", "jacobi"))
         self._ctx, self._slab = ctx, ss
-        conns_dev = ctx.to_device(conns_loc, torch.int64)      # this rank's throats only
+        # the Laplacian of an unchanged (network, conductance array) is kept on the device
+        # between runs (settings.cache, _transport.py:108-114); the verdict is collective
+        ckey = (id(ctx), id(self.network), g.__array_interface__["data"][0], g.size)
+        reuse = bool(self.settings["cache"]) and getattr(self, "_slab_cache_key", None) == ckey
+        flag = torch.tensor([1 if reuse else 0],
+                            device=ctx.tdev if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        reuse = bool(int(flag.item()))
+        conns_dev = self._slab_conns_dev if reuse else ctx.to_device(conns_loc, torch.int64)
+        self._slab_conns_dev = conns_dev                        # this rank's throats only
         if self.settings["validate_topology"]:
             # every rank labels the clusters of its own throats on its GPU; the cut
             # regions are joined on the host (dist.slab_topology_check)
@@ -437,9 +530,10 @@ class Transport(dict):
         self._update_hook(None)        # raises if a model needs the host (single-GPU only)
         try:
             srcs = self._sources()
-            f, nnz0, nnz = ss.assemble(conns_dev, self._slab_take(ctx, g, sel),
+            f, nnz0, nnz = ss.assemble(conns_dev, None if reuse else self._slab_take(ctx, g, sel),
                                        self["pore.bc.value"], self["pore.bc.rate"],
-                                       keep_zero_diag=len(srcs) > 0)
+                                       keep_zero_diag=len(srcs) > 0, reuse_laplacian=reuse)
+            self._slab_cache_key = ckey
             ctx.clear_sources()
             if solver._slab_p2p is None:              # maps the peers once (source-free operator)
                 solver._slab_p2p = ss.enable_p2p()
@@ -689,10 +783,24 @@ class ReactiveTransport(Transport):
         items = list(self["pore.source"].keys())
         host_items = [it for it in items if self._source_on_host(it, iterative)]
         g_variable = self.settings["conductance"] in iterative
+        self._gplan = None
         if not host_items and not g_variable:
             return None
         if self._world_size() > 1:
             raise NotImplementedError("host-evaluated models run on one GPU")
+        if g_variable and not host_items and self.settings.get("device_conductance", True):
+            plan = self._device_conductance_plan(iterative)
+            if plan is not None and ctx is not None:
+                # the whole chain has device kernels: the Picard loop re-evaluates g,
+                # re-assembles and re-applies the BCs itself, nothing comes back to the host
+                ctx.set_conductance_model(
+                    plan["kind"], self._device_conns(ctx), self.Np, plan["poly"],
+                    plan["size_factors"], throat_prop=plan["throat_prop"], interp=plan["interp"],
+                    bc_value=self["pore.bc.value"], bc_rate=self["pore.bc.rate"],
+                    keep_zero_diag=self._n_sources() > 0)
+                self._gplan = plan
+                self._cache_key = None
+                return None
         phase, q = self._phase, self.settings["quantity"]
         dev_items = [it for it in items if it not in host_items]
         device_terms = dict(zip(dev_items, self._sources_for(dev_items)))

@@ -55,9 +55,20 @@
 #define AMG_CHEB_RATIO 8.0
 #define AMG_COARSE_ITERS 30
 
+struct CsrOut {
+  DevBuf indptr, indices, data, dinv;
+  int64_t n = 0, nnz = 0;
+  // row-partitioned output of a pass in a slab run (columns are local signed ids:
+  // < 0 rank-1's rows, >= n rank+1's rows)
+  int64_t ng = 0, goff = 0, nnzg = 0;
+  int wlo = 0, whi = 0, slo = 0, shi = 0;
+};
+
 struct AmgLevel {
   int64_t n = 0, nnz = 0, nc = 0;       // rows / entries held by this rank; nc: rows of the next level
-  DevBuf indptr, indices, data, dinv;   // own CSR (levels >= 1)
+  CsrOut own;                           // levels >= 1: the rows this rank built (last pass's output)
+  CsrOut gath;                          // replicated level of a slab run: the gathered matrix
+  const double* dv = nullptr;           // 1 / diagonal of whichever of the two is live
   DevBuf dataf;                         // fp32 copy of the values for the cycle's products
   const int* ip = nullptr;
   const int* ix = nullptr;
@@ -77,15 +88,6 @@ struct AmgLevel {
   int64_t coff = 0;                     // offset of this rank's coarse rows in the next level
   double* xo() const { return x.as<double>() + wlo; }      // first owned entry of the padded vectors
   double* kc1o() const { return kc1.as<double>() + wlo; }
-};
-
-struct CsrOut {
-  DevBuf indptr, indices, data, dinv;
-  int64_t n = 0, nnz = 0;
-  // row-partitioned output of a pass in a slab run (columns are local signed ids:
-  // < 0 rank-1's rows, >= n rank+1's rows)
-  int64_t ng = 0, goff = 0, nnzg = 0;
-  int wlo = 0, whi = 0, slo = 0, shi = 0;
 };
 
 // the matrix a pairwise pass works on
@@ -110,7 +112,6 @@ struct AmgState {
   DevBuf t_match, t_prop, t_ids, t_cptr, t_cmem, t_tc, t_tv, t_aggpass, t_cnt, t_cur;
   DevBuf t_aggg, t_minmax, t_gcnt;      // slab runs: global ids of the halo'd map, column range, gather
   CsrOut t_csr[2];
-  CsrOut t_gather;
   // level 0 lives in the Jacobi-scaled, padded layout of the PCG operator
   DevBuf z0, z1, ax0, dir0, winv, fd, fq;
   DevBuf lmax_dev;
@@ -169,14 +170,15 @@ void b200_amg_release(b200_ctx* ctx) {
   if (!ctx->amg) return;
   AmgState* A = static_cast<AmgState*>(ctx->amg);
   for (AmgLevel& L : A->lv)
-    for (DevBuf* b : {&L.indptr, &L.indices, &L.data, &L.dinv, &L.agg, &L.cptr, &L.cmem, &L.x,
+    for (DevBuf* b : {&L.own.indptr, &L.own.indices, &L.own.data, &L.own.dinv, &L.gath.indptr,
+                      &L.gath.indices, &L.gath.data, &L.gath.dinv, &L.agg, &L.cptr, &L.cmem, &L.x,
                       &L.b, &L.ax, &L.dir, &L.kb, &L.kc1, &L.kv1, &L.kv2, &L.ks, &L.cgw, &L.dataf})
       b->release();
   for (DevBuf* b : {&A->z0, &A->z1, &A->ax0, &A->dir0, &A->winv, &A->fd, &A->fq, &A->lmax_dev,
                     &A->t_match, &A->t_prop, &A->t_ids, &A->t_cptr, &A->t_cmem, &A->t_tc, &A->t_tv,
                     &A->t_aggpass, &A->t_cnt, &A->t_cur, &A->t_aggg, &A->t_minmax, &A->t_gcnt})
     b->release();
-  for (CsrOut* c : {&A->t_csr[0], &A->t_csr[1], &A->t_gather})
+  for (CsrOut* c : {&A->t_csr[0], &A->t_csr[1]})
     for (DevBuf* b : {&c->indptr, &c->indices, &c->data, &c->dinv}) b->release();
   delete A;
   ctx->amg = nullptr;
@@ -1026,13 +1028,6 @@ static int amg_gather_level(b200_ctx* ctx, AmgState* A, const CsrOut& loc, CsrOu
   return B200_OK;
 }
 
-static void swap_csr(AmgLevel& C, CsrOut& o) {
-  std::swap(C.indptr, o.indptr);
-  std::swap(C.indices, o.indices);
-  std::swap(C.data, o.data);
-  std::swap(C.dinv, o.dinv);
-}
-
 static int amg_setup(b200_ctx* ctx) {
   AmgState* A = amg_of(ctx);
   A->valid = false;
@@ -1086,7 +1081,9 @@ static int amg_setup(b200_ctx* ctx) {
     CsrOut* last = nullptr;
     const int npass = (l == 0) ? amg_passes0() : AMG_PASSES;
     for (int pass = 0; pass < npass; ++pass) {
-      CsrOut& dst = A->t_csr[pass & 1];
+      // the last pass writes the next level's own buffers: nothing is reallocated
+      // when a hierarchy of the same shape is rebuilt
+      CsrOut& dst = (pass == npass - 1) ? A->lv[l + 1].own : A->t_csr[pass & 1];
       DevBuf& aggp = (pass == 0) ? A->lv[l].agg : A->t_aggpass;
       RET(amg_pair_pass(ctx, A, M, aggp, dst));
       if (dst.ng == 0) { ok = false; break; }
@@ -1123,24 +1120,23 @@ static int amg_setup(b200_ctx* ctx) {
     F.coff = last->goff;
     F.next_repl = false;
     RET(amg_members(ctx, A, n, (int)last->n, F.agg.as<int>(), F.cptr, F.cmem));
+    const CsrOut* live = last;
     if (F.dist && last->ng > repl_rows && last->ng > AMG_COARSEST) {
       // the next level stays row-partitioned
-      swap_csr(C, *last);
       C.dist = true;
       C.n = last->n; C.nnz = last->nnz; C.ng = last->ng; C.nnzg = last->nnzg;
       C.goff = last->goff;
       C.wlo = last->wlo; C.whi = last->whi; C.slo = last->slo; C.shi = last->shi;
     } else if (F.dist) {
       // small enough: every rank holds the next level (and everything below it) in full
-      RET(amg_gather_level(ctx, A, *last, A->t_gather));
-      swap_csr(C, A->t_gather);
+      RET(amg_gather_level(ctx, A, *last, C.gath));
+      live = &C.gath;
       F.next_repl = true;
       C.dist = false;
-      C.n = C.ng = A->t_gather.n; C.nnz = C.nnzg = A->t_gather.nnz;
+      C.n = C.ng = C.gath.n; C.nnz = C.nnzg = C.gath.nnz;
       C.goff = 0;
       C.wlo = C.whi = C.slo = C.shi = 0;
     } else {
-      swap_csr(C, *last);
       C.dist = false;
       C.n = C.ng = last->n; C.nnz = C.nnzg = last->nnz;
       C.goff = 0;
@@ -1148,9 +1144,10 @@ static int amg_setup(b200_ctx* ctx) {
     }
     C.next_repl = false;
     C.coff = 0;
-    C.ip = C.indptr.as<int>();
-    C.ix = C.indices.as<int>();
-    C.av = C.data.as<double>();
+    C.ip = live->indptr.as<int>();
+    C.ix = live->indices.as<int>();
+    C.av = live->data.as<double>();
+    C.dv = live->dinv.as<double>();
     RET(amg_level_bound(ctx, A, C, nullptr, 0));
     if (amg_f32()) {
       CK(C.dataf.ensure((size_t)(C.nnz > 0 ? C.nnz : 1) * sizeof(float)));
@@ -1270,11 +1267,11 @@ static int amg_cycle(b200_ctx* ctx, AmgState* A, size_t l, const double* b, doub
   const int64_t n = L.n;
   if (l + 1 == A->nlev) {
     double* w = L.cgw.as<double>();
-    LAUNCH(ctx, k_amg_coarse_cg, 1, 1024, 0, (int)n, L.ip, L.ix, L.av, L.dinv.as<double>(), b, x,
+    LAUNCH(ctx, k_amg_coarse_cg, 1, 1024, 0, (int)n, L.ip, L.ix, L.av, L.dv, b, x,
            w, w + n, w + 2 * n, AMG_COARSE_ITERS, 1e-2);
     return B200_OK;
   }
-  const double* dinv = (l == 0) ? nullptr : L.dinv.as<double>();
+  const double* dinv = (l == 0) ? nullptr : L.dv;
   const double* wgt = (l == 0) ? A->winv.as<double>() : nullptr;
   const int g = grid_for(n, AMG_T);
   // pre-smoothing, Chebyshev(2) from zero

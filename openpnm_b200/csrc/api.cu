@@ -50,7 +50,8 @@ extern "C" int b200_destroy(b200_ctx* ctx) {
                     &ctx->vx, &ctx->vr, &ctx->vp, &ctx->vap, &ctx->vb, &ctx->scal, &ctx->w_cnt,
                     &ctx->w_keys, &ctx->w_scan, &ctx->w_part, &ctx->w_ticket, &ctx->w_flags,
                     &ctx->w_tmp0, &ctx->w_tmp1, &ctx->w_tmp2, &ctx->vbi, &ctx->h_row, &ctx->h_col,
-                    &ctx->h_dat, &ctx->h_vec, &ctx->w_coll})
+                    &ctx->h_dat, &ctx->h_vec, &ctx->w_coll, &ctx->s_perm, &ctx->s_ptr,
+                    &ctx->s_cols, &ctx->s_vals, &ctx->gm_g})
     b->release();
   if (ctx->scal_h) cudaFreeHost(ctx->scal_h);
   if (ctx->flags_h) cudaFreeHost(ctx->flags_h);

@@ -892,3 +892,121 @@ extern "C" int b200_export_csr(b200_ctx* ctx, int which, int32_t* indptr, int32_
   CK(cudaStreamSynchronize(ctx->stream));
   return B200_OK;
 }
+
+
+// ===================================== conductance models on the device (f-3)
+// Replaces, inside the Picard loop, the host round trip of `_update_iterative_props`
+// (openpnm/algorithms/_algorithm.py:69-91) for the common chain
+//   quantity X -> pore transport property  P = sum_k a_k X^k   (models/misc: polynomial)
+//              -> throat value of it        Pt = given array, or mean / min / max of the
+//                                           two pores (models/misc: from_neighbor_pores)
+//              -> conduit conductance       generic_hydraulic
+//                                           (models/physics/hydraulic_conductance/_funcs.py:37-53:
+//                                            g_i = F_i / mu_i, series sum) or _poisson_conductance
+//                                           (models/physics/_utils.py:46-61: g_i = D_i F_i;
+//                                            generic_diffusive / thermal / electrical)
+// followed by the re-assembly (K1) and the BCs (K2).  Nothing leaves the device.
+struct PolyArg { double a[8]; int n; };
+
+__global__ void k_conduit_conductance(const longlong2* __restrict__ conns, int64_t Nt,
+                                      const double* __restrict__ x, PolyArg poly, int kind,
+                                      int interp, const double* __restrict__ throat_prop,
+                                      const double* __restrict__ sf, int sf_cols,
+                                      double* __restrict__ g) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < Nt; t += stride) {
+    const longlong2 c = conns[t];
+    double P[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const double X = x[s == 0 ? c.x : c.y];
+      double v = poly.a[poly.n - 1];
+      for (int k = poly.n - 2; k >= 0; --k) v = v * X + poly.a[k];     // Horner
+      P[s] = v;
+    }
+    double Pt;
+    if (throat_prop) Pt = throat_prop[t];
+    else if (interp == 1) Pt = fmin(P[0], P[1]);
+    else if (interp == 2) Pt = fmax(P[0], P[1]);
+    else Pt = 0.5 * (P[0] + P[1]);
+    double out;
+    if (sf_cols == 3) {
+      const double F1 = sf[3 * t], Ft = sf[3 * t + 1], F2 = sf[3 * t + 2];
+      double g1, gt, g2;
+      if (kind == B200_COND_HYDRAULIC) { g1 = F1 / P[0]; gt = Ft / Pt; g2 = F2 / P[1]; }
+      else { g1 = P[0] * F1; gt = Pt * Ft; g2 = P[1] * F2; }
+      out = 1.0 / (1.0 / g1 + 1.0 / gt + 1.0 / g2);
+    } else {
+      // one factor for the whole conduit: F1 = F2 = inf in generic_hydraulic, Dt F in
+      // _poisson_conductance
+      out = (kind == B200_COND_HYDRAULIC) ? 1.0 / (1.0 / (sf[t] / Pt)) : Pt * sf[t];
+    }
+    g[t] = out;
+  }
+}
+
+extern "C" int b200_set_conductance_model(b200_ctx* ctx, int kind, const int64_t* conns,
+                                          int64_t Nt, int64_t Np, const double* poly_h, int npoly,
+                                          int interp, const double* throat_prop,
+                                          const double* size_factors, int sf_cols,
+                                          const double* bc_value, const double* bc_rate,
+                                          int keep_zero_diag) {
+  if (!ctx) return B200_ERR_ARG;
+  if ((kind != B200_COND_HYDRAULIC && kind != B200_COND_POISSON) || !conns || !poly_h ||
+      npoly < 1 || npoly > 8 || interp < 0 || interp > 2 || !size_factors ||
+      (sf_cols != 1 && sf_cols != 3) || Nt <= 0 || Np <= 0)
+    FAIL(B200_ERR_ARG, "set_conductance_model: bad arguments");
+  if (ctx->nranks > 1) FAIL(B200_ERR_ARG, "set_conductance_model: single GPU only");
+  GModel& m = ctx->gm;
+  m.active = true;
+  m.kind = kind;
+  m.interp = interp;
+  m.npoly = npoly;
+  for (int k = 0; k < 8; ++k) m.poly[k] = k < npoly ? poly_h[k] : 0.0;
+  m.conns = conns;
+  m.Nt = Nt;
+  m.Np = Np;
+  m.throat_prop = throat_prop;
+  m.sf = size_factors;
+  m.sf_cols = sf_cols;
+  m.bcv = bc_value;
+  m.bcr = bc_rate;
+  m.keep_zero_diag = keep_zero_diag;
+  return B200_OK;
+}
+
+extern "C" int b200_clear_conductance_model(b200_ctx* ctx) {
+  if (!ctx) return B200_ERR_ARG;
+  ctx->gm.active = false;
+  return B200_OK;
+}
+
+// g(x) -> K1 -> K2 (x: device, Np entries).  Also usable on its own: the Picard loop
+// calls it before every linearisation while a model is set.
+extern "C" int b200_update_conductance(b200_ctx* ctx, const double* x) {
+  if (!ctx || !x) return B200_ERR_ARG;
+  GModel& m = ctx->gm;
+  if (!m.active) FAIL(B200_ERR_ARG, "update_conductance: no model set");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->gm_g.ensure((size_t)m.Nt * sizeof(double)));
+  PolyArg pa;
+  for (int k = 0; k < 8; ++k) pa.a[k] = m.poly[k];
+  pa.n = m.npoly;
+  LAUNCH(ctx, k_conduit_conductance, grid_for(m.Nt, 256), 256, 0,
+         reinterpret_cast<const longlong2*>(m.conns), m.Nt, x, pa, m.kind, m.interp,
+         m.throat_prop, m.sf, m.sf_cols, ctx->gm_g.as<double>());
+  CK(cudaGetLastError());
+  int64_t nnz = 0;
+  RET(build_laplacian_impl(ctx, m.conns, ctx->gm_g.as<double>(), 0, m.Np, m.Nt, 0, m.Np, &nnz));
+  double f = 0.0;
+  return b200_apply_bcs(ctx, m.bcv, m.bcr, m.keep_zero_diag, &f, &nnz);
+}
+
+extern "C" int b200_conductance_values(b200_ctx* ctx, double* g_out) {
+  if (!ctx || !g_out) return B200_ERR_ARG;
+  if (!ctx->gm.active || !ctx->gm_g.p) FAIL(B200_ERR_ARG, "conductance_values: no model evaluated");
+  CK(cudaMemcpyAsync(g_out, ctx->gm_g.p, (size_t)ctx->gm.Nt * sizeof(double),
+                     cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}

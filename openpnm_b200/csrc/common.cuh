@@ -11,7 +11,7 @@
 #include "b200pnm.h"
 
 #define B200_MAX_SRC 8
-#define B200_MAX_DIAGS 8
+#define B200_MAX_DIAGS 13     // Cubic(connectivity=26) has 13 super-diagonals
 
 struct DevBuf {
   void* p = nullptr;
@@ -85,6 +85,20 @@ struct P2PState {
   unsigned long long seq = 0;
 };
 
+// Conductance that follows the quantity, evaluated on the device inside the Picard loop
+// (assembly.cu: b200_set_conductance_model).  All pointers are caller-owned device arrays.
+struct GModel {
+  bool active = false;
+  int kind = 0, interp = 0, npoly = 0, sf_cols = 1, keep_zero_diag = 0;
+  double poly[8] = {};
+  const int64_t* conns = nullptr;
+  int64_t Nt = 0, Np = 0;
+  const double* throat_prop = nullptr;
+  const double* sf = nullptr;
+  const double* bcv = nullptr;
+  const double* bcr = nullptr;
+};
+
 struct b200_ctx {
   int device = 0;
   int num_sms = 148;
@@ -137,6 +151,11 @@ struct b200_ctx {
   DevBuf dia_store;
   DevBuf o_indptr, o_cols, o_vals, o_rowstart;  // scaled off-diagonal CSR
   int64_t o_nnz = 0, o_nblocks = 0, o_maxrow = 0;
+  // the same operator as sliced ELLPACK (SELL-32-sigma): rows sorted by length inside
+  // windows of SELL_SIGMA rows, 32 rows per slice stored column-major (solver.cu)
+  DevBuf s_perm, s_ptr, s_cols, s_vals;
+  int64_t s_nslices = 0, s_entries = 0;
+  bool use_sell = false, sell_staged = true;
   DevBuf vx, vr, vp, vap, vb;  // PCG vectors (padded layout)
   DevBuf vbi;                  // BiCGStab extras: rhat, s (padded), t
   DevBuf scal;                 // SC_COUNT doubles
@@ -147,6 +166,9 @@ struct b200_ctx {
   int* flags_h = nullptr;      // pinned
   DevBuf h_row, h_col, h_dat, h_vec;   // device staging of b200_solve_coo_h
   DevBuf w_coll;                       // staging of the small host-visible collectives (dist.cu)
+
+  GModel gm;
+  DevBuf gm_g;                 // conductances of the last evaluation of the model
 
   // preconditioner: B200_PRECOND_JACOBI or B200_PRECOND_AMG (amg.cu owns `amg`)
   int precond = 0;
@@ -296,6 +318,8 @@ bool b200_p2p_usable(b200_ctx* ctx);
 int b200_p2p_iteration(b200_ctx* ctx, double* gin, double* gout, bool true_norm, bool wait_halo,
                        bool rr_is_global, const double* d);
 int b200_p2p_check(b200_ctx* ctx);
+// assembly.cu
+int b200_update_conductance(b200_ctx* ctx, const double* x);
 // solver.cu
 int b200_linearize(b200_ctx* ctx, const double* x);
 int b200_residual_norms(b200_ctx* ctx, const double* x, double* res2, double* x2);

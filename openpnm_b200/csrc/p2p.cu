@@ -364,7 +364,7 @@ int b200_p2p_iteration(b200_ctx* ctx, double* gin, double* gout, bool true_norm,
   } break;
   switch (ctx->dia.nd) {
     P2P_CASE(1) P2P_CASE(2) P2P_CASE(3) P2P_CASE(4) P2P_CASE(5) P2P_CASE(6) P2P_CASE(7)
-    P2P_CASE(8)
+    P2P_CASE(8) P2P_CASE(9) P2P_CASE(10) P2P_CASE(11) P2P_CASE(12) P2P_CASE(13)
     default: FAIL(B200_ERR_ARG, "bad diagonal count");
   }
 #undef P2P_CASE

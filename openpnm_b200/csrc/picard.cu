@@ -78,6 +78,14 @@ static int picard_update(b200_ctx* ctx, b200_update_fn update, void* user, const
     CK(ctx->w_tmp0.ensure((size_t)n * sizeof(double)));
     CK(ctx->w_part.ensure((size_t)4 * 148 * 16 * sizeof(double)));
   }
+  if (ctx->gm.active) {
+    // conductance model on the device: g(x) -> K1 -> K2, no host round trip.  The
+    // sources registered on the context survive (they live outside the system matrix).
+    RET(b200_update_conductance(ctx, x));
+    if (ctx->n != n) FAIL(B200_ERR_ARG, "picard: the conductance model changed the system size");
+    CK(ctx->w_tmp0.ensure((size_t)n * sizeof(double)));
+    CK(ctx->w_part.ensure((size_t)4 * 148 * 16 * sizeof(double)));
+  }
   return b200_linearize(ctx, x);
 }
 

@@ -8,7 +8,7 @@
 //   openpnm/models/physics/source_terms/_funcs.py:21-168 linearised sources
 //
 // Operator formats (the PCG never touches the canonical CSR again):
-//   DIA  : the matrix has <= 8 distinct super-diagonals (any lattice network in
+//   DIA  : the matrix has <= 13 distinct super-diagonals (any lattice network in
 //          index order).  Symmetric half storage: one fp64 array per
 //          super-diagonal, no indices, unit main diagonal implied.
 //          y_i = x_i + sum_m v_m[i] x[i+k_m] + v_m[i-k_m] x[i-k_m]
@@ -19,6 +19,7 @@
 // reads i +/- k never need a bounds check; in slab mode the pads are the
 // halo windows filled by the neighbour ranks.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include <algorithm>
@@ -236,11 +237,14 @@ __global__ void k_detect_offsets(const int* __restrict__ indptr, const int* __re
   int mymax = 0;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
     const int64_t gi = r + rb;
+    // once the table has overflowed (an irregular network) only the bandwidth is
+    // still wanted: skip the slot search, which would hammer one cache line
+    const bool full = *reinterpret_cast<volatile int*>(&tab->overflow) != 0;
     for (int e = indptr[r]; e < indptr[r + 1]; ++e) {
       const int64_t o64 = (int64_t)indices[e] - gi;
       const int ao = (int)(o64 < 0 ? -o64 : o64);
       if (ao > mymax) mymax = ao;
-      if (o64 == 0) continue;
+      if (o64 == 0 || full) continue;
       // |offset| of lower entries too: in a slab a lower entry may point below
       // the owned rows while no owned row has the mirrored upper entry
       const int o = ao;
@@ -375,6 +379,68 @@ __global__ void k_rowstart(const int* __restrict__ optr, int64_t n, int64_t Q, i
     if ((int64_t)optr[mid] + mid >= target) hi = mid; else lo = mid + 1;
   }
   rowstart[q] = (int)lo;
+}
+
+// ---- SELL-32-sigma build (irregular networks).  Inside every window of SELL_SIGMA
+// consecutive rows the rows are sorted by descending length (bitonic sort of
+// (length, index) keys in shared memory: deterministic), 32 sorted rows form a slice
+// whose width is its first row's length; entries are stored column-major inside the
+// slice, so a warp reads 32 consecutive values / columns per step and no reduction
+// across lanes is needed.  Padding entries multiply 0.0 by the row's own p.
+#define SELL_SIGMA 1024
+#define SELL_C 32
+__global__ void __launch_bounds__(SELL_SIGMA) k_sell_sort(const int* __restrict__ optr, int64_t n,
+                                                          int* __restrict__ perm,
+                                                          int* __restrict__ swidth) {
+  __shared__ unsigned key[SELL_SIGMA];
+  const int64_t base = (int64_t)blockIdx.x * SELL_SIGMA;
+  const int t = threadIdx.x;
+  const int64_t r = base + t;
+  // ascending sort of (0x1fffff - len) << 10 | t  ==  descending length, ascending index
+  unsigned k = 0xffffffffu;
+  if (r < n) {
+    const int len = optr[r + 1] - optr[r];
+    k = ((unsigned)(0x1fffff - len) << 10) | (unsigned)t;
+  }
+  key[t] = k;
+  __syncthreads();
+  for (int size = 2; size <= SELL_SIGMA; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const int partner = t ^ stride;
+      if (partner > t) {
+        const unsigned a = key[t], b = key[partner];
+        const bool up = (t & size) == 0;
+        if ((a > b) == up) { key[t] = b; key[partner] = a; }
+      }
+      __syncthreads();
+    }
+  const unsigned kk = key[t];
+  const bool valid = kk != 0xffffffffu;
+  perm[base + t] = valid ? (int)(base + (kk & 1023u)) : -1;
+  if ((t & (SELL_C - 1)) == 0)
+    swidth[(base + t) / SELL_C] = valid ? (int)(0x1fffff - (kk >> 10)) * SELL_C : 0;
+}
+
+__global__ void __launch_bounds__(256) k_sell_fill(const int* __restrict__ optr,
+                                                   const int* __restrict__ ocols,
+                                                   const double* __restrict__ ovals,
+                                                   const int* __restrict__ perm,
+                                                   const int* __restrict__ sptr, int64_t nslices,
+                                                   int* __restrict__ scols,
+                                                   double* __restrict__ svals) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < nslices; s += wstride) {
+    const int b = sptr[s], width = (sptr[s + 1] - b) / SELL_C;
+    const int r = perm[s * SELL_C + lane];
+    const int e0 = r >= 0 ? optr[r] : 0, len = r >= 0 ? optr[r + 1] - e0 : 0;
+    const int self = r >= 0 ? r : 0;
+    for (int k = 0; k < width; ++k) {
+      const bool in = k < len;
+      scols[b + k * SELL_C + lane] = in ? ocols[e0 + k] : self;
+      svals[b + k * SELL_C + lane] = in ? ovals[e0 + k] : 0.0;
+    }
+  }
 }
 
 #ifndef CSR_Q
@@ -524,6 +590,29 @@ static int prepare_operator(b200_ctx* ctx) {
     LAUNCH(ctx, k_rowstart, (int)((ctx->o_nblocks + 1 + 255) / 256), 256, 0,
            ctx->o_indptr.as<int>(), n, (int64_t)CSR_Q, ctx->o_nblocks, ctx->o_rowstart.as<int>());
     ctx->fmt = B200_FMT_CSR;
+    // sliced-ELL copy of the same operator (B200_CSR_KERNEL=stream keeps the
+    // shared-memory CSR-stream kernel for A/B runs)
+    const char* ek = getenv("B200_CSR_KERNEL");
+    ctx->use_sell = !(ek && ek[0] == 's' && ek[1] == 't') && maxrow < 0x1fffff && n > 0;
+    ctx->sell_staged = !(ek && strcmp(ek, "sell0") == 0);   // sell0: plain SELL, no staging
+    if (ctx->use_sell) {
+      const int64_t nwin = (n + SELL_SIGMA - 1) / SELL_SIGMA;
+      const int64_t nsl = nwin * (SELL_SIGMA / SELL_C);
+      CK(ctx->s_perm.ensure((size_t)(nwin * SELL_SIGMA) * sizeof(int)));
+      CK(ctx->w_cnt.ensure((size_t)(nsl + 1) * sizeof(int)));
+      CK(ctx->s_ptr.ensure((size_t)(nsl + 1) * sizeof(int)));
+      LAUNCH(ctx, k_sell_sort, (int)nwin, SELL_SIGMA, 0, ctx->o_indptr.as<int>(), n,
+             ctx->s_perm.as<int>(), ctx->w_cnt.as<int>());
+      int64_t sent = 0;
+      RET(b200_scan_exclusive_i32(ctx, ctx->w_cnt.as<int>(), ctx->s_ptr.as<int>(), nsl, &sent));
+      CK(ctx->s_cols.ensure((size_t)(sent + 32) * sizeof(int)));
+      CK(ctx->s_vals.ensure((size_t)(sent + 32) * sizeof(double)));
+      LAUNCH(ctx, k_sell_fill, grid_for(nsl * 32, 256), 256, 0, ctx->o_indptr.as<int>(),
+             ctx->o_cols.as<int>(), ctx->o_vals.as<double>(), ctx->s_perm.as<int>(),
+             ctx->s_ptr.as<int>(), nsl, ctx->s_cols.as<int>(), ctx->s_vals.as<double>());
+      ctx->s_nslices = nsl;
+      ctx->s_entries = sent;
+    }
   }
   CK(cudaGetLastError());
   ctx->op_epoch = ctx->sys_epoch;
@@ -685,11 +774,136 @@ int b200_dia_smooth(b200_ctx* ctx, int mode, const double* p_owned, const double
   } break;
   switch (ctx->dia.nd) {
     SM_CASE(1) SM_CASE(2) SM_CASE(3) SM_CASE(4) SM_CASE(5) SM_CASE(6) SM_CASE(7) SM_CASE(8)
+    SM_CASE(9) SM_CASE(10) SM_CASE(11) SM_CASE(12) SM_CASE(13)
     default: FAIL(B200_ERR_ARG, "bad diagonal count");
   }
 #undef SM_CASE
   CK(cudaGetLastError());
   return B200_OK;
+}
+
+// ---- K_A (SELL-32-sigma): one warp per slice, one row per lane; every step of the
+// slice loop reads 32 consecutive values (256 B) and columns (128 B) and gathers p
+// through L1/L2; four independent chains per lane keep the loads in flight.  The row's
+// own p, r and Ap are scattered inside the sorting window (<= SELL_SIGMA rows: 8 KB).
+template <bool UNIT>
+__global__ void __launch_bounds__(PCG_T) k_sell_spmv_dot(
+    const int* __restrict__ sptr, const int* __restrict__ scols, const double* __restrict__ svals,
+    const int* __restrict__ perm, int64_t nslices, const double* __restrict__ p,
+    const double* __restrict__ rv, const double* __restrict__ dexp, double* __restrict__ ap,
+    double* part, unsigned* ticket, double* out_pap) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double dot = 0.0, dot2 = 0.0, dotr = 0.0;
+  for (int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < nslices; s += wstride) {
+    const int b = sptr[s], width = (sptr[s + 1] - b) >> 5;
+    const int r = perm[s * SELL_C + lane];
+    const int* c = scols + b + lane;
+    const double* v = svals + b + lane;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = 0;
+    for (; k + 4 <= width; k += 4) {
+      const int c0 = c[(k + 0) * SELL_C], c1 = c[(k + 1) * SELL_C], c2 = c[(k + 2) * SELL_C],
+                c3 = c[(k + 3) * SELL_C];
+      const double v0 = v[(k + 0) * SELL_C], v1 = v[(k + 1) * SELL_C], v2 = v[(k + 2) * SELL_C],
+                   v3 = v[(k + 3) * SELL_C];
+      a0 += v0 * p[c0];
+      a1 += v1 * p[c1];
+      a2 += v2 * p[c2];
+      a3 += v3 * p[c3];
+    }
+    for (; k < width; ++k) a0 += v[k * SELL_C] * p[c[k * SELL_C]];
+    if (r >= 0) {
+      const double pi = p[r];
+      const double acc = (UNIT ? pi : dexp[r] * pi) + ((a0 + a1) + (a2 + a3));
+      ap[r] = acc;
+      dot += pi * acc;
+      dotr += rv[r] * acc;
+      dot2 += acc * acc;
+    }
+  }
+  double vv[3] = {dot, dotr, dot2};
+  double* o[3] = {out_pap + G_PAP, out_pap + G_RAP, out_pap + G_APAP};
+  grid_sum_finalize<3>(vv, part, ticket, o);
+}
+
+// ---- K_A (SELL-32-sigma, staged operand): one CTA per sorting window of SELL_SIGMA rows.
+// The slice of p the window's rows mostly read -- their own rows +- SELL_W -- is loaded
+// coalesced into shared memory first, so a gather costs a shared-memory read instead of
+// a 32-byte sector from L2 (columns outside the staged range fall back to global
+// memory; with the pores numbered along a space-filling curve inside coordinate bins,
+// dist.spatial_order, ~85 % of the columns are inside).  Row results go through
+// shared memory too, so Ap is written and r is read coalesced for the three dot
+// products.  North star: "shared-memory staging of x".
+template <bool UNIT, int W, int UNR>
+__global__ void __launch_bounds__(PCG_T, (UNR >= 16 ? 2 : UNR >= 8 ? 4 : 5)) k_sell_spmv_dot_w(
+    const int* __restrict__ sptr, const int* __restrict__ scols, const double* __restrict__ svals,
+    const int* __restrict__ perm, int64_t nwin, int64_t n, int64_t pad,
+    const double* __restrict__ p, const double* __restrict__ rv, const double* __restrict__ dexp,
+    double* __restrict__ ap, double* part, unsigned* ticket, double* out_pap) {
+  extern __shared__ double sm[];
+  double* pw = sm;                                  // p[lo .. lo + SIGMA + 2W)
+  double* accw = sm + SELL_SIGMA + 2 * W;           // row sums of the window
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = PCG_T / 32, SPW = SELL_SIGMA / SELL_C;
+  double dot = 0.0, dot2 = 0.0, dotr = 0.0;
+  for (int64_t win = blockIdx.x; win < nwin; win += gridDim.x) {
+    const int64_t r0 = win * SELL_SIGMA, lo = r0 - W;
+    for (int i = threadIdx.x; i < SELL_SIGMA + 2 * W; i += PCG_T) {
+      const int64_t idx = lo + i;
+      pw[i] = (idx >= -pad && idx < n + pad) ? p[idx] : 0.0;
+    }
+    __syncthreads();
+    const int ilo = (int)lo;
+#define SELL_GET(cc) (((unsigned)((cc) - ilo) < (unsigned)(SELL_SIGMA + 2 * W)) ? pw[(cc) - ilo] : p[cc])
+    for (int sl = warp; sl < SPW; sl += NW) {
+      const int64_t s = win * SPW + sl;
+      const int b = sptr[s], width = (sptr[s + 1] - b) >> 5;
+      const int r = perm[s * SELL_C + lane];
+      const int* c = scols + b + lane;
+      const double* v = svals + b + lane;
+      double a[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) a[u] = 0.0;
+      int k = 0;
+      // tiers of UNR, then 4, then single steps: every tier issues all its column and
+      // value loads before the first gather (memory-level parallelism is what this
+      // kernel lives on: ncu shows it latency-bound, not bandwidth-bound)
+#define SELL_TIER(T)                                                          \
+      for (; k + (T) <= width; k += (T)) {                                    \
+        int cc[T];                                                            \
+        double vv[T];                                                         \
+        _Pragma("unroll") for (int u = 0; u < (T); ++u) cc[u] = c[(k + u) * SELL_C];   \
+        _Pragma("unroll") for (int u = 0; u < (T); ++u) vv[u] = v[(k + u) * SELL_C];   \
+        _Pragma("unroll") for (int u = 0; u < (T); ++u) a[u] += vv[u] * SELL_GET(cc[u]); \
+      }
+      SELL_TIER(UNR)
+      if (UNR > 4) { SELL_TIER(4) }
+      SELL_TIER(1)
+#undef SELL_TIER
+      double tot = 0.0;
+#pragma unroll
+      for (int u = UNR - 1; u >= 0; --u) tot += a[u];
+      if (r >= 0) accw[r - r0] = tot;
+    }
+#undef SELL_GET
+    __syncthreads();
+    for (int i = threadIdx.x; i < SELL_SIGMA; i += PCG_T) {
+      const int64_t r = r0 + i;
+      if (r < n) {
+        const double pi = pw[i + W];
+        const double acc = (UNIT ? pi : dexp[r] * pi) + accw[i];
+        ap[r] = acc;
+        dot += pi * acc;
+        dotr += rv[r] * acc;
+        dot2 += acc * acc;
+      }
+    }
+    __syncthreads();
+  }
+  double vv3[3] = {dot, dotr, dot2};
+  double* o[3] = {out_pap + G_PAP, out_pap + G_RAP, out_pap + G_APAP};
+  grid_sum_finalize<3>(vv3, part, ticket, o);
 }
 
 // ---- K_A (CSR-stream): vals/cols streamed coalesced into shared memory as
@@ -957,10 +1171,63 @@ static int launch_spmv_dot(b200_ctx* ctx, const double* p_owned, const double* r
   } break;
     switch (ctx->dia.nd) {
       DIA_CASE(1) DIA_CASE(2) DIA_CASE(3) DIA_CASE(4) DIA_CASE(5) DIA_CASE(6) DIA_CASE(7)
-      DIA_CASE(8)
+      DIA_CASE(8) DIA_CASE(9) DIA_CASE(10) DIA_CASE(11) DIA_CASE(12) DIA_CASE(13)
       default: FAIL(B200_ERR_ARG, "bad diagonal count");
     }
 #undef DIA_CASE
+  } else if (ctx->use_sell && ctx->sell_staged && n + 2 * ctx->pad < (1ll << 31) - 8192) {
+    const int64_t nwin = ctx->s_nslices / (SELL_SIGMA / SELL_C);
+    int64_t g = nwin < 148 * 16 ? nwin : 148 * 16;
+    if (g < 1) g = 1;
+    static int variant = -1;      // tuning knob: B200_SELL_VARIANT = 0..5 (default 3: W 512, unroll 8)
+    if (variant < 0) {
+      const char* e = getenv("B200_SELL_VARIANT");
+      variant = (e && e[0] >= '0' && e[0] <= '5') ? e[0] - '0' : 3;
+    }
+#define SELL_LAUNCH(W, UNR)                                                                   \
+  {                                                                                           \
+    const size_t smem = (size_t)(2 * SELL_SIGMA + 2 * (W)) * sizeof(double);                   \
+    static bool attr = false;                                                                 \
+    if (!attr) {                                                                              \
+      CK(cudaFuncSetAttribute(k_sell_spmv_dot_w<true, W, UNR>,                                \
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+      CK(cudaFuncSetAttribute(k_sell_spmv_dot_w<false, W, UNR>,                               \
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+      attr = true;                                                                            \
+    }                                                                                         \
+    if (ctx->unit_diag)                                                                       \
+      LAUNCH(ctx, (k_sell_spmv_dot_w<true, W, UNR>), (int)g, PCG_T, smem, ctx->s_ptr.as<int>(), \
+             ctx->s_cols.as<int>(), ctx->s_vals.as<double>(), ctx->s_perm.as<int>(), nwin, n, \
+             ctx->pad, p_owned, r_owned, dexp, ap_owned, part, ticket, out);                  \
+    else                                                                                      \
+      LAUNCH(ctx, (k_sell_spmv_dot_w<false, W, UNR>), (int)g, PCG_T, smem, ctx->s_ptr.as<int>(), \
+             ctx->s_cols.as<int>(), ctx->s_vals.as<double>(), ctx->s_perm.as<int>(), nwin, n, \
+             ctx->pad, p_owned, r_owned, dexp, ap_owned, part, ticket, out);                  \
+  }
+    if (variant == 1) SELL_LAUNCH(1024, 8)
+    else if (variant == 2) SELL_LAUNCH(512, 4)
+    else if (variant == 3) SELL_LAUNCH(512, 8)
+    else if (variant == 4) SELL_LAUNCH(512, 16)
+    else if (variant == 5) SELL_LAUNCH(256, 8)
+    else SELL_LAUNCH(1024, 4)
+#undef SELL_LAUNCH
+  } else if (ctx->use_sell) {
+    static int occ = 0;
+    if (!occ) {
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sell_spmv_dot<true>, PCG_T, 0));
+      if (occ < 1) occ = 1;
+    }
+    int64_t g = (ctx->s_nslices * 32 + PCG_T - 1) / PCG_T;
+    if (g > (int64_t)occ * ctx->num_sms) g = (int64_t)occ * ctx->num_sms;
+    if (g < 1) g = 1;
+    if (ctx->unit_diag)
+      LAUNCH(ctx, k_sell_spmv_dot<true>, (int)g, PCG_T, 0, ctx->s_ptr.as<int>(),
+             ctx->s_cols.as<int>(), ctx->s_vals.as<double>(), ctx->s_perm.as<int>(),
+             ctx->s_nslices, p_owned, r_owned, dexp, ap_owned, part, ticket, out);
+    else
+      LAUNCH(ctx, k_sell_spmv_dot<false>, (int)g, PCG_T, 0, ctx->s_ptr.as<int>(),
+             ctx->s_cols.as<int>(), ctx->s_vals.as<double>(), ctx->s_perm.as<int>(),
+             ctx->s_nslices, p_owned, r_owned, dexp, ap_owned, part, ticket, out);
   } else if (ctx->o_maxrow <= CSR_MAXROW) {
     const size_t smem = (size_t)(CSR_Q + ctx->o_maxrow + 1) * sizeof(double);
     const int nb = (int)ctx->o_nblocks;
@@ -1215,6 +1482,28 @@ extern "C" int b200_pcg(b200_ctx* ctx, const double* x0, double rtol, double ato
   if (iters) *iters = it;
   if (relres) *relres = rel;
   if (info) *info = inf;
+  return B200_OK;
+}
+
+// bytes one K_A launch has to move in the storage format in use (what the roofline
+// fraction "on format bytes" divides by): operator + p, r read + Ap written
+extern "C" int b200_operator_bytes(b200_ctx* ctx, int64_t* bytes, int64_t* entries) {
+  if (!ctx || !bytes) return B200_ERR_ARG;
+  if (ctx->fmt == B200_FMT_NONE) FAIL(B200_ERR_ARG, "operator_bytes: run b200_pcg_prepare first");
+  const int64_t n = ctx->n;
+  int64_t b = 24 * n, e = 0;
+  if (ctx->fmt == B200_FMT_DIA) {
+    b += (int64_t)ctx->dia.nd * 8 * n;
+    e = (int64_t)ctx->dia.nd * n;
+  } else if (ctx->use_sell) {
+    b += 12 * ctx->s_entries + 4 * ctx->s_nslices * SELL_C + 4 * ctx->s_nslices;
+    e = ctx->s_entries;
+  } else {
+    b += 12 * ctx->o_nnz + 4 * n;
+    e = ctx->o_nnz;
+  }
+  *bytes = b;
+  if (entries) *entries = e;
   return B200_OK;
 }
 

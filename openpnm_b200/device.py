@@ -355,6 +355,51 @@ class Context:
                                    self._p(x), C.byref(it), C.byref(rel), C.byref(info)))
         return self._publish(x), it.value, rel.value, info.value
 
+    def set_conductance_model(self, kind, conns, Np, poly, size_factors, throat_prop=None,
+                              interp="mean", bc_value=None, bc_rate=None, keep_zero_diag=False):
+        """Conductance that follows the quantity, evaluated on the device inside the Picard
+        loop (b200_set_conductance_model).  kind: 'hydraulic' (generic_hydraulic) or
+        'poisson' (_poisson_conductance); poly: coefficients a_k of the pore property."""
+        torch = _torch()
+        conns = self.to_device(conns, torch.int64)
+        Nt = int(conns.numel() // 2)
+        sf = np.ascontiguousarray(size_factors, dtype=np.float64)
+        cols = 3 if sf.ndim == 2 else 1
+        if sf.shape[0] != Nt or (sf.ndim == 2 and sf.shape[1] != 3):
+            raise ValueError("size factors must be (Nt,) or (Nt, 3)")
+        sf_d = self.to_device(sf.reshape(-1), torch.float64)
+        tp = self.to_device(np.ascontiguousarray(throat_prop, dtype=np.float64),
+                            torch.float64) if throat_prop is not None else None
+        bv = self.to_device(bc_value, torch.float64) if bc_value is not None else None
+        br = self.to_device(bc_rate, torch.float64) if bc_rate is not None else None
+        a = np.ascontiguousarray(poly, dtype=np.float64)
+        self._ck(self.lib.b200_set_conductance_model(
+            self._h, {"hydraulic": 0, "poisson": 1}[kind], self._p(conns), Nt, int(Np),
+            _lib.np_ptr(a), int(a.size), {"mean": 0, "min": 1, "max": 2}[interp], self._p(tp),
+            self._p(sf_d), cols, self._p(bv), self._p(br), 1 if keep_zero_diag else 0))
+        self._keep["gmodel"] = (conns, sf_d, tp, bv, br)
+        self._keep["conns"] = conns
+        self._gmodel_Nt = Nt
+
+    def clear_conductance_model(self):
+        self._ck(self.lib.b200_clear_conductance_model(self._h))
+        self._keep.pop("gmodel", None)
+
+    def update_conductance(self, x):
+        """g(x) -> K1 -> K2 with the model that is set; returns nothing (the system on the
+        device is the re-assembled one)."""
+        torch = _torch()
+        x = self.to_device(x, torch.float64)
+        self._ck(self.lib.b200_update_conductance(self._h, self._p(x)))
+        self.n = int(x.numel())
+
+    def conductance_values(self):
+        torch = _torch()
+        g = self.empty(self._gmodel_Nt, torch.float64)
+        self._ck(self.lib.b200_conductance_values(self._h, self._p(g)))
+        self._keep["g"] = g
+        return self._publish(g)
+
     def clear_sources(self):
         self._ck(self.lib.b200_clear_sources(self._h))
         self._keep["src"] = []
@@ -460,6 +505,12 @@ class Context:
         ms = C.c_double()
         self._ck(self.lib.b200_time_kernel(self._h, int(which), int(reps), C.byref(ms)))
         return ms.value
+
+    def operator_bytes(self):
+        """(bytes one K_A launch moves in the format in use, stored entries)"""
+        b, e = C.c_int64(), C.c_int64()
+        self._ck(self.lib.b200_operator_bytes(self._h, C.byref(b), C.byref(e)))
+        return b.value, e.value
 
     def stats(self):
         s = _lib.Stats()

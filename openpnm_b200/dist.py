@@ -22,7 +22,7 @@ import numpy as np
 
 __all__ = ["slab_ranges", "cubic_slab_ranges", "slab_throat_mask", "cubic_slab_throats",
            "cubic_slab_throat_ranges",
-           "bandwidth", "coordinate_order", "SlabSolver", "init_process_group",
+           "bandwidth", "coordinate_order", "spatial_order", "SlabSolver", "init_process_group",
            "slab_topology_check", "join_slab_clusters"]
 
 
@@ -131,6 +131,41 @@ def coordinate_order(coords, axis=0):
     perm = np.argsort(np.asarray(coords)[:, axis], kind="stable")
     inv = np.empty_like(perm)
     inv[perm] = np.arange(perm.size)
+    return perm, inv
+
+
+def _spread3(v):
+    """10 bits -> every third bit (Morton interleave helper)"""
+    v = v.astype(np.uint64) & np.uint64(0x3ff)
+    v = (v | (v << np.uint64(16))) & np.uint64(0x30000ff)
+    v = (v | (v << np.uint64(8))) & np.uint64(0x300f00f)
+    v = (v | (v << np.uint64(4))) & np.uint64(0x30c30c3)
+    v = (v | (v << np.uint64(2))) & np.uint64(0x9249249)
+    return v
+
+
+def spatial_order(coords, axis=0, blocks=64):
+    """Renumbering for irregular networks that keeps BOTH properties the slab solver
+    wants: pores are ordered by `blocks` equal-count bins along `axis` first (so the
+    index bandwidth stays ~2/blocks of Np and contiguous index ranges are still
+    coordinate slabs), and along a Morton (Z-order) curve inside each bin, so that
+    the neighbours of a pore have nearby indices and the gathers of the SpMV hit
+    L1/L2 lines that were just used.  Returns (perm, inverse) like coordinate_order."""
+    c = np.asarray(coords, dtype=np.float64)
+    n = c.shape[0]
+    by_axis = np.argsort(c[:, axis], kind="stable")
+    bin_of = np.empty(n, dtype=np.int64)
+    bin_of[by_axis] = (np.arange(n, dtype=np.int64) * blocks) // max(n, 1)
+    lo, hi = c.min(axis=0), c.max(axis=0)
+    q = ((c - lo) / np.where(hi > lo, hi - lo, 1.0) * 1023.0).astype(np.uint64)
+    # the binned axis varies least inside a bin: give it the low interleave position
+    others = [a for a in range(c.shape[1]) if a != axis]
+    code = _spread3(q[:, axis])
+    for k, a in enumerate(others[:2]):
+        code |= _spread3(q[:, a]) << np.uint64(k + 1)
+    perm = np.lexsort((code, bin_of))
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(n)
     return perm, inv
 
 
@@ -247,11 +282,19 @@ class SlabSolver:
             self.ctx._ck(self.ctx.lib.b200_comm_init(self.ctx._h, self.world, self.rank,
                                                      C.cast(idbuf, C.c_void_p)))
 
-    def assemble(self, conns_local, g_local, bc_value=None, bc_rate=None, keep_zero_diag=False):
+    def assemble(self, conns_local, g_local, bc_value=None, bc_rate=None, keep_zero_diag=False,
+                 reuse_laplacian=False):
+        """reuse_laplacian: the pure Laplacian (and the global diagonal mean) built by the
+        previous call are still valid -- only the BCs are applied again (the reference's
+        `settings.cache`, _transport.py:108-114)."""
         import torch
         import torch.distributed as dist
         ctx = self.ctx
+        if reuse_laplacian and getattr(self, "_nnz_pure", None) is not None:
+            f, nnz_sys = ctx.apply_bcs(bc_value, bc_rate, keep_zero_diag=keep_zero_diag)
+            return f, self._nnz_pure, nnz_sys
         nnz = ctx.build_laplacian(conns_local, g_local, self.Np, self.row_begin, self.row_end)
+        self._nnz_pure = nnz
         if self.world > 1:
             s, c = ctx.pure_diag_sum()
             t = torch.tensor([s, float(c)], dtype=torch.float64)

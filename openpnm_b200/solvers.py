@@ -65,13 +65,15 @@ class B200PCG(IterativeSolver):
         ``openpnm_b200`` algorithms split the network into slabs over the ranks.
     fmt : {'auto', 'csr', 'dia'}
         Operator storage; 'auto' picks symmetric-diagonal storage when the
-        matrix has at most 8 distinct super-diagonals (lattice networks).
+        matrix has at most 13 distinct super-diagonals (lattice networks, up to
+        Cubic(connectivity=26)).
     precond : {'jacobi', 'amg'}
         'amg' preconditions the CG with an aggregation-multigrid K-cycle built
         on the device (the role `PyamgRugeStubenSolver` plays in the reference,
         solvers/_pyamg.py:10-17): tens of iterations at any size instead of
-        O(N) on an N^3 lattice.  Same stopping rule; symmetric systems on one
-        GPU with more than 2048 unknowns, Jacobi otherwise.
+        O(N) on an N^3 lattice.  Same stopping rule; symmetric systems with more
+        than 2048 unknowns (slab runs under torchrun included: one hierarchy whose
+        levels are row-partitioned by the slabs), Jacobi otherwise.
 
     Returns from ``solve``: ``(x, exit_code)`` with SciPy's convention --
     0 converged, >0 maxiter reached, <0 breakdown (matrix not SPD).

@@ -68,6 +68,33 @@ def test_reference_stokesflow_with_b200_multigrid(op, b2):
     # before the parity files have run
 
 
+@pytest.mark.parametrize("conn,nd", [(14, 7), (18, 9), (26, 13)])
+def test_reference_cubic_with_diagonal_neighbours(op, b2, conn, nd):
+    """`Cubic(connectivity=14/18/26)` (openpnm/_skgraph/generators/_cubic.py:40-67): 7 / 9 / 13
+    super-diagonals, all on the implicit-index DIA fast path (B200_MAX_DIAGS = 13)."""
+    pn = op.network.Cubic(shape=[12, 11, 10], spacing=1e-4, connectivity=conn)
+    ph = op.phase.Phase(network=pn)
+    ph["throat.hydraulic_conductance"] = hetero(pn.Nt, conn)
+    sf = op.algorithms.StokesFlow(network=pn, phase=ph)
+    sf.set_value_BC(pores=pn.pores("left"), values=2e5)
+    sf.set_value_BC(pores=pn.pores("right"), values=1e5)
+    sf.run(solver=op.solvers.ScipySpsolve())
+    x_ref = np.array(sf.x)
+    for precond in ("jacobi", "amg"):
+        solver = b2.B200PCG(tol=1e-13, precond=precond)
+        sf.run(solver=solver)
+        assert sf.soln.is_converged
+        assert np.max(np.abs(sf.x - x_ref) / np.abs(x_ref)) < 1e-8
+        assert solver.info["fmt"] == "dia" and solver.info["ndiags"] == nd
+    # the same network through the B200 algorithm (device assembly), forced to the
+    # general sliced-ELL operator: same answer
+    alg = b2.StokesFlow(network=pn, phase=ph)
+    alg.set_value_BC(pores=pn.pores("left"), values=2e5)
+    alg.set_value_BC(pores=pn.pores("right"), values=1e5)
+    alg.run(solver=b2.B200PCG(tol=1e-13, fmt="csr"))
+    assert np.max(np.abs(alg.x - x_ref) / np.abs(x_ref)) < 1e-8
+
+
 def test_default_solver_registration(op, b2):
     """op.Workspace().settings.default_solver = 'B200PCG' (utils/_workspace.py:44-56)."""
     b2.register_with_openpnm(op)

@@ -422,3 +422,74 @@ def test_variable_conductance(b2):
     # net flow is conserved with the final conductance
     nt.assert_allclose(alg.rate(pores=net.pores("front"))[0],
                        -alg.rate(pores=net.pores("back"))[0], rtol=1e-5)
+
+
+def _variable_g_case(b2, device):
+    """diffusivity = polynomial of the concentration, throat value = mean of the pores,
+    conductance = generic_diffusive with (Nt,3) size factors: the chain that has device
+    kernels (b200_set_conductance_model); device=False forces the host hook instead."""
+    rng = np.random.default_rng(4)
+    net = b2.Cubic(shape=[6, 5, 4])
+    net["throat.diffusive_size_factors"] = rng.uniform(0.5, 2.0, (net.Nt, 3)) * 1e-3
+    phase = b2.Phase(net)
+    phase["pore.concentration"] = 0.0
+
+    def polynomial(target, a, prop):          # openpnm/models/misc/_simple_equations.py:88-117
+        x = target[prop].astype(float)
+        return sum(a[i] * x ** i for i in range(len(a)))
+
+    def from_neighbor_pores(target, prop, mode="min"):
+        v = target[prop][target.network.conns]
+        return {"min": v.min(axis=1), "max": v.max(axis=1), "mean": v.mean(axis=1)}[mode]
+
+    def generic_diffusive(target, pore_diffusivity="pore.diffusivity",
+                          throat_diffusivity="throat.diffusivity",
+                          size_factors="throat.diffusive_size_factors"):
+        cn = target.network.conns       # models/physics/_utils.py:46-61
+        Dt = target[throat_diffusivity]
+        D1, D2 = target[pore_diffusivity][cn].T
+        F1, Ft, F2 = target.network[size_factors].T
+        return 1 / (1 / (D1 * F1) + 1 / (Dt * Ft) + 1 / (D2 * F2))
+
+    phase.add_model(propname="pore.diffusivity", model=polynomial,
+                    a=[1e-9, 0.0, 5e-11], prop="pore.concentration")
+    phase.add_model(propname="throat.diffusivity", model=from_neighbor_pores,
+                    prop="pore.diffusivity", mode="mean")
+    phase.add_model(propname="throat.diffusive_conductance", model=generic_diffusive,
+                    pore_diffusivity="pore.diffusivity", throat_diffusivity="throat.diffusivity",
+                    size_factors="throat.diffusive_size_factors")
+    phase.regenerate_models()
+    alg = b2.ReactiveTransport(network=net, phase=phase)
+    alg.settings._update({"conductance": "throat.diffusive_conductance",
+                          "quantity": "pore.concentration", "device_conductance": device})
+    alg.set_value_BC(pores=net.pores("front"), values=10.0)
+    alg.set_value_BC(pores=net.pores("back"), values=0.0)
+    return net, phase, alg
+
+
+def test_variable_conductance_on_the_device(b2):
+    """g(x) through polynomial -> from_neighbor_pores -> generic_diffusive is
+    evaluated, re-assembled and re-linearised on the device; same iterates as the host
+    hook (the reference's `_update_iterative_props` path), phase left as regenerate_models
+    leaves it."""
+    out = {}
+    for device in (False, True):
+        net, phase, alg = _variable_g_case(b2, device)
+        assert alg.iterative_props == ["pore.diffusivity", "throat.diffusivity",
+                                       "throat.diffusive_conductance"]
+        plan = alg._device_conductance_plan(alg.iterative_props)
+        assert plan is not None and plan["kind"] == "poisson" and plan["interp"] == "mean"
+        alg.run(solver=b2.B200PCG(tol=1e-13))
+        assert alg.soln.is_converged and alg.soln.num_iter > 2
+        out[device] = (np.array(alg.x), alg.soln.num_iter,
+                       np.array(phase["throat.diffusive_conductance"]),
+                       alg.rate(pores=net.pores("front"))[0])
+        launches = alg.stats["kernel_launches"]
+    assert out[True][1] == out[False][1]                      # same outer iterations
+    nt.assert_allclose(out[True][0], out[False][0], rtol=1e-9, atol=1e-12)
+    nt.assert_allclose(out[True][2], out[False][2], rtol=1e-9)   # final g on the phase
+    nt.assert_allclose(out[True][3], out[False][3], rtol=1e-8)
+    # the nonlinearity bites: the profile is not the linear one
+    c = out[True][0].reshape(6, 5, 4).mean(axis=(0, 2))
+    nt.assert_allclose([c[0], c[-1]], [10.0, 0.0], atol=1e-9)
+    assert abs(c[2] - 5.0) > 0.3, c
