@@ -93,34 +93,47 @@ __device__ __forceinline__ bool grid_sum_last(const double (&v)[NV], double* par
 }
 
 template <int ND>
-__global__ void __launch_bounds__(P2P_T) k_dia_spmv_dot_p2p(DiaPack A, const double* __restrict__ p,
+__global__ void __launch_bounds__(P2P_T) k_dia_spmv_dot_p2p(DiaPack A, const double* p,
                                                             const double* __restrict__ rv,
                                                             double* __restrict__ ap, int64_t n,
                                                             double* part, unsigned* ticket,
                                                             double* gin, P2PArgs a) {
   __shared__ double tot[3];
-  if (a.wait_halo) {
-    if (threadIdx.x == 0) {
-      if (a.rank > 0) spin_until_ge(&a.flags[0], a.wait_halo, a.flags);
-      if (a.rank < a.nranks - 1) spin_until_ge(&a.flags[1], a.wait_halo, a.flags);
-    }
-    __syncthreads();
-  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   double dot = 0.0, dot2 = 0.0, dotr = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const double pi = p[i];
-    double acc = pi;
-#pragma unroll
-    for (int m = 0; m < ND; ++m) {
-      const int64_t k = A.off[m];
-      acc += A.v[m][i] * p[i + k];
-      acc += A.v[m][i - k] * p[i - k];
+  // Interior rows first: they read no halo entry, so nobody waits for a neighbour
+  // before ~98 % of the rows are done; only then does each block look at the halo
+  // flags (usually long since set) and take its share of the 2 * halo edge rows.
+  // The halo windows are written by the peers' K_BC: read them around the cache
+  // hierarchy's non-coherent path (plain loads of `p`, which is not __restrict__ here).
+  const int64_t h = a.wait_halo ? a.halo : 0;          // no wait: the halo is already in place
+  int64_t ilo = (a.rank > 0) ? h : 0, ihi = (a.rank < a.nranks - 1) ? n - h : n;
+  if (ihi < ilo) ilo = ihi = 0;                        // slab thinner than 2 halos: all rows wait
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) {
+      if (ilo == 0 && ihi == n) break;
+      if (threadIdx.x == 0) {
+        if (a.rank > 0) spin_until_ge(&a.flags[0], a.wait_halo, a.flags);
+        if (a.rank < a.nranks - 1) spin_until_ge(&a.flags[1], a.wait_halo, a.flags);
+      }
+      __syncthreads();
     }
-    ap[i] = acc;
-    dot += pi * acc;
-    dotr += rv[i] * acc;
-    dot2 += acc * acc;
+    const int64_t cnt = pass == 0 ? ihi - ilo : ilo + (n - ihi);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += stride) {
+      const int64_t i = pass == 0 ? ilo + q : (q < ilo ? q : ihi + (q - ilo));
+      const double pi = p[i];
+      double acc = pi;
+#pragma unroll
+      for (int m = 0; m < ND; ++m) {
+        const int64_t k = A.off[m];
+        acc += A.v[m][i] * p[i + k];
+        acc += A.v[m][i - k] * p[i - k];
+      }
+      ap[i] = acc;
+      dot += pi * acc;
+      dotr += rv[i] * acc;
+      dot2 += acc * acc;
+    }
   }
   double v[3] = {dot, dotr, dot2};
   double* o[3] = {gin + G_PAP, gin + G_RAP, gin + G_APAP};
@@ -319,7 +332,15 @@ int b200_p2p_check(b200_ctx* ctx) {
   unsigned long long e = 0;
   CK(cudaMemcpyAsync(&e, ctx->p2p.flags + 2, sizeof e, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  if (e) FAIL(B200_ERR_NCCL, "p2p: a peer did not answer in time (spin limit reached)");
+  if (e) {
+    // a timed-out exchange leaves mailboxes and sequence numbers in an unknown state:
+    // clear the flag and stop using the fused path on this context (the NCCL back end
+    // takes over at the next solve) instead of failing every later solve as well
+    CK(cudaMemsetAsync(ctx->p2p.flags + 2, 0, sizeof(unsigned long long), ctx->stream));
+    ctx->p2p.ready = false;
+    FAIL(B200_ERR_NCCL, "p2p: a peer did not answer in time (spin limit reached); "
+                        "fused communication disabled for this context");
+  }
   return B200_OK;
 }
 

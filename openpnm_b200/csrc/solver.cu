@@ -835,8 +835,8 @@ __global__ void __launch_bounds__(PCG_T) k_sell_spmv_dot(
 // dist.spatial_order, ~85 % of the columns are inside).  Row results go through
 // shared memory too, so Ap is written and r is read coalesced for the three dot
 // products.  North star: "shared-memory staging of x".
-template <bool UNIT, int W, int UNR>
-__global__ void __launch_bounds__(PCG_T, (UNR >= 16 ? 2 : UNR >= 8 ? 4 : 5)) k_sell_spmv_dot_w(
+template <bool UNIT, int W, int UNR, int T>
+__global__ void __launch_bounds__(T, (UNR >= 16 ? 2 : UNR >= 8 ? 4 : 5) * (256 / T)) k_sell_spmv_dot_w(
     const int* __restrict__ sptr, const int* __restrict__ scols, const double* __restrict__ svals,
     const int* __restrict__ perm, int64_t nwin, int64_t n, int64_t pad,
     const double* __restrict__ p, const double* __restrict__ rv, const double* __restrict__ dexp,
@@ -845,11 +845,11 @@ __global__ void __launch_bounds__(PCG_T, (UNR >= 16 ? 2 : UNR >= 8 ? 4 : 5)) k_s
   double* pw = sm;                                  // p[lo .. lo + SIGMA + 2W)
   double* accw = sm + SELL_SIGMA + 2 * W;           // row sums of the window
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NW = PCG_T / 32, SPW = SELL_SIGMA / SELL_C;
+  constexpr int NW = T / 32, SPW = SELL_SIGMA / SELL_C;
   double dot = 0.0, dot2 = 0.0, dotr = 0.0;
   for (int64_t win = blockIdx.x; win < nwin; win += gridDim.x) {
     const int64_t r0 = win * SELL_SIGMA, lo = r0 - W;
-    for (int i = threadIdx.x; i < SELL_SIGMA + 2 * W; i += PCG_T) {
+    for (int i = threadIdx.x; i < SELL_SIGMA + 2 * W; i += T) {
       const int64_t idx = lo + i;
       pw[i] = (idx >= -pad && idx < n + pad) ? p[idx] : 0.0;
     }
@@ -888,7 +888,7 @@ __global__ void __launch_bounds__(PCG_T, (UNR >= 16 ? 2 : UNR >= 8 ? 4 : 5)) k_s
     }
 #undef SELL_GET
     __syncthreads();
-    for (int i = threadIdx.x; i < SELL_SIGMA; i += PCG_T) {
+    for (int i = threadIdx.x; i < SELL_SIGMA; i += T) {
       const int64_t r = r0 + i;
       if (r < n) {
         const double pi = pw[i + W];
@@ -1179,37 +1179,38 @@ static int launch_spmv_dot(b200_ctx* ctx, const double* p_owned, const double* r
     const int64_t nwin = ctx->s_nslices / (SELL_SIGMA / SELL_C);
     int64_t g = nwin < 148 * 16 ? nwin : 148 * 16;
     if (g < 1) g = 1;
-    static int variant = -1;      // tuning knob: B200_SELL_VARIANT = 0..5 (default 3: W 512, unroll 8)
+    static int variant = -1;      // tuning knob: B200_SELL_VARIANT = 0..5 (default 4: staged window +-256,
+                                  // unroll 8, 128-thread CTAs: best of the measured set, profiles/README.md)
     if (variant < 0) {
       const char* e = getenv("B200_SELL_VARIANT");
-      variant = (e && e[0] >= '0' && e[0] <= '5') ? e[0] - '0' : 3;
+      variant = (e && e[0] >= '0' && e[0] <= '5') ? e[0] - '0' : 4;
     }
-#define SELL_LAUNCH(W, UNR)                                                                   \
+#define SELL_LAUNCH(W, UNR, T)                                                                \
   {                                                                                           \
     const size_t smem = (size_t)(2 * SELL_SIGMA + 2 * (W)) * sizeof(double);                   \
     static bool attr = false;                                                                 \
     if (!attr) {                                                                              \
-      CK(cudaFuncSetAttribute(k_sell_spmv_dot_w<true, W, UNR>,                                \
+      CK(cudaFuncSetAttribute(k_sell_spmv_dot_w<true, W, UNR, T>,                             \
                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-      CK(cudaFuncSetAttribute(k_sell_spmv_dot_w<false, W, UNR>,                               \
+      CK(cudaFuncSetAttribute(k_sell_spmv_dot_w<false, W, UNR, T>,                            \
                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
       attr = true;                                                                            \
     }                                                                                         \
     if (ctx->unit_diag)                                                                       \
-      LAUNCH(ctx, (k_sell_spmv_dot_w<true, W, UNR>), (int)g, PCG_T, smem, ctx->s_ptr.as<int>(), \
+      LAUNCH(ctx, (k_sell_spmv_dot_w<true, W, UNR, T>), (int)g, T, smem, ctx->s_ptr.as<int>(), \
              ctx->s_cols.as<int>(), ctx->s_vals.as<double>(), ctx->s_perm.as<int>(), nwin, n, \
              ctx->pad, p_owned, r_owned, dexp, ap_owned, part, ticket, out);                  \
     else                                                                                      \
-      LAUNCH(ctx, (k_sell_spmv_dot_w<false, W, UNR>), (int)g, PCG_T, smem, ctx->s_ptr.as<int>(), \
+      LAUNCH(ctx, (k_sell_spmv_dot_w<false, W, UNR, T>), (int)g, T, smem, ctx->s_ptr.as<int>(), \
              ctx->s_cols.as<int>(), ctx->s_vals.as<double>(), ctx->s_perm.as<int>(), nwin, n, \
              ctx->pad, p_owned, r_owned, dexp, ap_owned, part, ticket, out);                  \
   }
-    if (variant == 1) SELL_LAUNCH(1024, 8)
-    else if (variant == 2) SELL_LAUNCH(512, 4)
-    else if (variant == 3) SELL_LAUNCH(512, 8)
-    else if (variant == 4) SELL_LAUNCH(512, 16)
-    else if (variant == 5) SELL_LAUNCH(256, 8)
-    else SELL_LAUNCH(1024, 4)
+    if (variant == 1) SELL_LAUNCH(1024, 8, 256)
+    else if (variant == 2) SELL_LAUNCH(512, 8, 128)
+    else if (variant == 4) SELL_LAUNCH(256, 8, 128)
+    else if (variant == 5) SELL_LAUNCH(512, 8, 64)
+    else if (variant == 0) SELL_LAUNCH(1024, 4, 256)
+    else SELL_LAUNCH(512, 8, 256)
 #undef SELL_LAUNCH
   } else if (ctx->use_sell) {
     static int occ = 0;
