@@ -78,6 +78,28 @@ def _host_copy(src, min_chunk=1 << 21):
     return dst
 
 
+class _Stages:
+    """Host-side stage timer of run(): active only with B200_PROFILE=1 (it synchronises
+    the stream at every mark, which the normal path must not do)."""
+
+    def __init__(self, ctx):
+        import os
+        self.on = os.environ.get("B200_PROFILE") == "1"
+        self.ctx, self.t, self.out = ctx, None, {}
+        if self.on:
+            import time
+            self.clock = time.perf_counter
+            ctx.synchronize()
+            self.t = self.clock()
+
+    def mark(self, name):
+        if self.on:
+            self.ctx.synchronize()
+            now = self.clock()
+            self.out[name] = self.out.get(name, 0.0) + 1e3 * (now - self.t)
+            self.t = now
+
+
 class SolutionContainer(dict):
     """openpnm/algorithms/_solution.py:10"""
     pass
@@ -293,8 +315,8 @@ class Transport(dict):
         msg = "Your network is clustered, making Ax = b ill-conditioned"
         if ctx is not None:
             conns = self._device_conns(ctx)
-            _, nbad = ctx.check_topology(conns, self.Np, self["pore.bc.value"],
-                                         self["pore.bc.rate"])
+            bv, br = self._device_bcs(ctx)
+            _, nbad = ctx.check_topology(conns, self.Np, bv, br)
             if nbad:
                 raise Exception(msg)
             return
@@ -318,10 +340,28 @@ class Transport(dict):
         import torch
         conns = np.asarray(self.network["throat.conns"], dtype=np.int64)
         key = (id(ctx), conns.__array_interface__["data"][0], conns.shape[0])
+        memo = getattr(self, "_run_memo", None)       # one upload per run() even with cache off
+        if memo is not None and memo.get("conns_key") == key:
+            return memo["conns"]
         if not self.settings["cache"] or getattr(self, "_conns_key", None) != key:
             self._conns_dev = ctx.to_device(conns, torch.int64)
             self._conns_key = key
+        if memo is not None:
+            memo["conns_key"], memo["conns"] = key, self._conns_dev
         return self._conns_dev
+
+    def _device_bcs(self, ctx):
+        """'pore.bc.value' / 'pore.bc.rate' on the device, uploaded once per run() (the
+        topology check and the BC kernel both read them)."""
+        import torch
+        memo = getattr(self, "_run_memo", None)
+        if memo is not None and "bcs" in memo:
+            return memo["bcs"]
+        out = (ctx.to_device(self["pore.bc.value"], torch.float64),
+               ctx.to_device(self["pore.bc.rate"], torch.float64))
+        if memo is not None:
+            memo["bcs"] = out
+        return out
 
     # ------------------------------------------------------------- solve
     def _sources(self):
@@ -343,8 +383,8 @@ class Transport(dict):
         if not (self.settings["cache"] and self._cache_key == key):
             ctx.build_laplacian(self._device_conns(ctx), g, self.Np)
             self._cache_key = key
-        f, nnz = ctx.apply_bcs(self["pore.bc.value"], self["pore.bc.rate"],
-                               keep_zero_diag=self._n_sources() > 0)
+        bv, br = self._device_bcs(ctx)
+        f, nnz = ctx.apply_bcs(bv, br, keep_zero_diag=self._n_sources() > 0)
         return f, nnz
 
     def run(self, solver=None, x0=None, verbose=False):
@@ -372,10 +412,14 @@ class Transport(dict):
         ctx = solver.ctx
         self._ctx = ctx
         ctx.set_format(solver._fmt_code())
+        self._run_memo = {}
+        st = _Stages(ctx)
         if self.settings["validate_topology"]:
             self._validate_topology_health(ctx)
+        st.mark("topology")
         try:
             self._assemble(ctx)
+            st.mark("upload+assemble")
             ctx.clear_sources()
             for mask, kind, p1, p2, p3 in self._sources():
                 ctx.add_source(kind, mask, p1, p2, p3)
@@ -395,8 +439,10 @@ class Transport(dict):
             if e.code == -4:
                 raise Exception("A or b contains inf/nan values") from e
             raise
+        st.mark("picard+solve")
         self._x_dev = x_dev
         x = self._download(ctx, x_dev)
+        st.mark("download")
         q = self.settings["quantity"]
         if getattr(self, "_gplan", None) is not None:
             # leave the phase as regenerate_models would at the converged x
@@ -417,6 +463,10 @@ class Transport(dict):
         if not conv:
             logger.warning(f"{self.name} didn't converge after {num_iter} iterations")
         self._post_run(x)
+        st.mark("post")
+        self._run_memo = None
+        if st.on:
+            self.stats["host_stage_ms"] = st.out
 
     def _post_run(self, x):
         pass
@@ -519,21 +569,26 @@ class Transport(dict):
                             device=ctx.tdev if dist.get_backend() == "nccl" else "cpu")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         reuse = bool(int(flag.item()))
+        st = _Stages(ctx)
         conns_dev = self._slab_conns_dev if reuse else ctx.to_device(conns_loc, torch.int64)
         self._slab_conns_dev = conns_dev                        # this rank's throats only
+        bv_dev = self._slab_bc_dev(ctx, "pore.bc.value", rb, re, band)
+        br_dev = self._slab_bc_dev(ctx, "pore.bc.rate", rb, re, band)
+        st.mark("upload conns+bcs")
         if self.settings["validate_topology"]:
             # every rank labels the clusters of its own throats on its GPU; the cut
             # regions are joined on the host (dist.slab_topology_check)
-            if bdist.slab_topology_check(ctx, conns_dev, self.Np, rb, re, band,
-                                         self["pore.bc.value"], self["pore.bc.rate"]):
+            if bdist.slab_topology_check(ctx, conns_dev, self.Np, rb, re, band, bv_dev, br_dev):
                 raise Exception("Your network is clustered, making Ax = b ill-conditioned")
+        st.mark("topology")
         self._update_hook(None)        # raises if a model needs the host (single-GPU only)
         try:
             srcs = self._sources()
             f, nnz0, nnz = ss.assemble(conns_dev, None if reuse else self._slab_take(ctx, g, sel),
-                                       self["pore.bc.value"], self["pore.bc.rate"],
+                                       bv_dev, br_dev,
                                        keep_zero_diag=len(srcs) > 0, reuse_laplacian=reuse)
             self._slab_cache_key = ckey
+            st.mark("upload g+assemble")
             ctx.clear_sources()
             if solver._slab_p2p is None:              # maps the peers once (source-free operator)
                 solver._slab_p2p = ss.enable_p2p()
@@ -553,9 +608,12 @@ class Transport(dict):
             if e.code == -4:
                 raise Exception("A or b contains inf/nan values") from e
             raise
+        st.mark("picard+solve")
         x_dev = ss.gather(x_loc)
         self._x_dev = x_dev
+        st.mark("gather")
         x = self._download(ctx, x_dev)
+        st.mark("download")
         q = self.settings["quantity"]
         dict.__setitem__(self, q, x)
         self.soln[q] = SteadyStateSolution(x)
@@ -566,6 +624,9 @@ class Transport(dict):
         self.stats = ctx.stats()
         self.soln.relres = self.stats["relres"]
         self._post_run(x)
+        st.mark("post")
+        if st.on:
+            self.stats["host_stage_ms"] = st.out
 
     def _slab_plan(self, world, rank):
         """(row_begin, row_end, index bandwidth, selector of this rank's throats, their
@@ -605,6 +666,24 @@ class Transport(dict):
         out = (rb, re, band, sel, conns_loc)
         self._slab_plan_cache = (key, out)
         return out
+
+    def _slab_bc_dev(self, ctx, key, rb, re, band):
+        """Global-length BC array on this rank's device of which only the part the rank
+        reads -- its rows and the halo columns, [rb - band, re + band) -- is uploaded;
+        the rest of the (persistent) buffer stays NaN = "no BC" and is never looked at."""
+        import torch
+        cache = self.__dict__.setdefault("_slab_bc_cache", {})
+        ck = (id(ctx), key, self.Np)
+        buf = cache.get(ck)
+        if buf is None:
+            with torch.cuda.stream(ctx.stream):
+                buf = torch.full((self.Np,), float("nan"), dtype=torch.float64, device=ctx.tdev)
+            cache[ck] = buf
+        lo, hi = max(rb - band, 0), min(re + band, self.Np)
+        src = np.ascontiguousarray(self[key][lo:hi], dtype=np.float64)
+        with torch.cuda.stream(ctx.stream):
+            buf[lo:hi].copy_(torch.from_numpy(src), non_blocking=True)
+        return buf
 
     def _slab_take(self, ctx, a, sel):
         """Per-throat array of this rank's throats on the device: `sel` is either an
@@ -1054,6 +1133,7 @@ class TransientReactiveTransport(ReactiveTransport):
         self._validate_settings()
         ctx = integrator.ctx
         self._ctx = ctx
+        self._run_memo = {}
         ctx.set_format(integrator._fmt_code())
         if self.settings["validate_topology"]:
             self._validate_topology_health(ctx)

@@ -296,6 +296,8 @@ void b200_comm_release(b200_ctx* ctx);
 // solver.cu helpers used by transient.cu / bicgstab.cu
 int b200_spmv_dots(b200_ctx* ctx, const double* w_owned, const double* rv_owned,
                    double* out_owned, double* group);
+int b200_spmv_dots_rows(b200_ctx* ctx, const double* p_owned, const double* r_owned,
+                        double* ap_owned, double* group, int64_t hi0, int64_t lo1);
 int b200_launch_init(b200_ctx* ctx, const double* x0, double* xt, double* bt, double* out_b2);
 int b200_launch_resid(b200_ctx* ctx, const double* bt, const double* ap, const double* d,
                       double* r, double* p, double* out_rr, double* out_true);

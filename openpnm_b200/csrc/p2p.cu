@@ -17,6 +17,8 @@
 // different GPUs and only ever wait for data a *previous* kernel of the peer
 // produced, so there is no circular wait; every spin is bounded and raises an
 // error flag instead of hanging.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define P2P_T 256
@@ -92,52 +94,57 @@ __device__ __forceinline__ bool grid_sum_last(const double (&v)[NV], double* par
   return is_last;
 }
 
+// K_A of the fused iteration is two launches: the rows that read no halo entry go
+// through the ordinary K_A (solver.cu: k_dia_spmv_dot, same code and speed as on one
+// GPU) without waiting for anybody; this kernel then waits for the neighbours' halo
+// flags -- usually long since set, the interior is ~98 % of the rows -- does the
+// 2 * halo edge rows, adds its sums to the interior's and its last block publishes the
+// rank's totals to every peer's mailbox.  The halo windows are written by the peers'
+// K_BC while this rank may already be computing: the edge rows read p with
+// ld.global.cg (from L2, where peer stores land) after the acquire on the flag, never
+// through the read-only path.  rows: [0, hi0) and [lo1, n); empty ranges = publish only.
 template <int ND>
-__global__ void __launch_bounds__(P2P_T) k_dia_spmv_dot_p2p(DiaPack A, const double* p,
-                                                            const double* __restrict__ rv,
-                                                            double* __restrict__ ap, int64_t n,
-                                                            double* part, unsigned* ticket,
-                                                            double* gin, P2PArgs a) {
+__global__ void __launch_bounds__(P2P_T) k_dia_edges_p2p(DiaPack A, const double* p,
+                                                         const double* __restrict__ rv,
+                                                         double* __restrict__ ap, int64_t n,
+                                                         int64_t hi0, int64_t lo1, double* part,
+                                                         unsigned* ticket, double* gin, P2PArgs a) {
   __shared__ double tot[3];
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  double dot = 0.0, dot2 = 0.0, dotr = 0.0;
-  // Interior rows first: they read no halo entry, so nobody waits for a neighbour
-  // before ~98 % of the rows are done; only then does each block look at the halo
-  // flags (usually long since set) and take its share of the 2 * halo edge rows.
-  // The halo windows are written by the peers' K_BC: read them around the cache
-  // hierarchy's non-coherent path (plain loads of `p`, which is not __restrict__ here).
-  const int64_t h = a.wait_halo ? a.halo : 0;          // no wait: the halo is already in place
-  int64_t ilo = (a.rank > 0) ? h : 0, ihi = (a.rank < a.nranks - 1) ? n - h : n;
-  if (ihi < ilo) ilo = ihi = 0;                        // slab thinner than 2 halos: all rows wait
-  for (int pass = 0; pass < 2; ++pass) {
-    if (pass == 1) {
-      if (ilo == 0 && ihi == n) break;
-      if (threadIdx.x == 0) {
-        if (a.rank > 0) spin_until_ge(&a.flags[0], a.wait_halo, a.flags);
-        if (a.rank < a.nranks - 1) spin_until_ge(&a.flags[1], a.wait_halo, a.flags);
-      }
-      __syncthreads();
+  if (a.wait_halo) {
+    if (threadIdx.x == 0) {
+      if (a.rank > 0) spin_until_ge(&a.flags[0], a.wait_halo, a.flags);
+      if (a.rank < a.nranks - 1) spin_until_ge(&a.flags[1], a.wait_halo, a.flags);
     }
-    const int64_t cnt = pass == 0 ? ihi - ilo : ilo + (n - ihi);
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += stride) {
-      const int64_t i = pass == 0 ? ilo + q : (q < ilo ? q : ihi + (q - ilo));
-      const double pi = p[i];
-      double acc = pi;
-#pragma unroll
-      for (int m = 0; m < ND; ++m) {
-        const int64_t k = A.off[m];
-        acc += A.v[m][i] * p[i + k];
-        acc += A.v[m][i - k] * p[i - k];
-      }
-      ap[i] = acc;
-      dot += pi * acc;
-      dotr += rv[i] * acc;
-      dot2 += acc * acc;
-    }
+    __syncthreads();
   }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t cnt = hi0 + (n - lo1);
+  double dot = 0.0, dot2 = 0.0, dotr = 0.0;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += stride) {
+    const int64_t i = q < hi0 ? q : lo1 + (q - hi0);
+    const double pi = __ldcg(p + i);
+    double acc = pi;
+#pragma unroll
+    for (int m = 0; m < ND; ++m) {
+      const int64_t k = A.off[m];
+      acc += A.v[m][i] * __ldcg(p + i + k);
+      acc += A.v[m][i - k] * __ldcg(p + i - k);
+    }
+    ap[i] = acc;
+    dot += pi * acc;
+    dotr += rv[i] * acc;
+    dot2 += acc * acc;
+  }
+  // add the interior's sums (written by the previous launch) in a fixed order
   double v[3] = {dot, dotr, dot2};
+  double part_int[3] = {gin[G_PAP], gin[G_RAP], gin[G_APAP]};
   double* o[3] = {gin + G_PAP, gin + G_RAP, gin + G_APAP};
   if (grid_sum_last<3>(v, part, ticket, o, tot)) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { tot[k] += part_int[k]; *o[k] = tot[k]; }
+    }
+    __syncthreads();
     if (threadIdx.x < a.nranks) {
       double rrc = gin[G_RR], trc = gin[G_TRUE];
       if (a.rr_global && a.rank != 0) { rrc = 0.0; trc = 0.0; }
@@ -370,18 +377,26 @@ int b200_p2p_iteration(b200_ctx* ctx, double* gin, double* gout, bool true_norm,
   double* r = ctx->vr.as<double>() + pad;
   double* p = ctx->vp.as<double>() + pad;
   double* ap = ctx->vap.as<double>() + pad;
+  // interior rows: the ordinary K_A, nobody waits; with no halo to wait for (first
+  // iteration after an NCCL exchange) it takes all rows and the edge kernel only publishes
+  int64_t hi0 = 0, lo1 = n;
+  if (a.wait_halo && n > 2 * ctx->halo) {
+    hi0 = ctx->rank > 0 ? ctx->halo : 0;
+    lo1 = ctx->rank < ctx->nranks - 1 ? n - ctx->halo : n;
+    RET(b200_spmv_dots_rows(ctx, p, r, ap, gin, hi0, lo1));
+  } else if (!a.wait_halo) {
+    RET(b200_spmv_dots_rows(ctx, p, r, ap, gin, 0, n));
+  } else {
+    hi0 = n;                      // slab thinner than two halos: every row waits
+    CK(cudaMemsetAsync(gin, 0, 3 * sizeof(double), ctx->stream));
+  }
 #define P2P_CASE(ND)                                                                        \
   case ND: {                                                                                \
-    static int occ = 0;                                                                     \
-    if (!occ) {                                                                             \
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dia_spmv_dot_p2p<ND>, P2P_T, \
-                                                       0));                                 \
-      if (occ < 1) occ = 1;                                                                 \
-    }                                                                                       \
-    int64_t g = (n + P2P_T - 1) / P2P_T;                                                    \
-    if (g > (int64_t)occ * ctx->num_sms) g = (int64_t)occ * ctx->num_sms;                   \
-    LAUNCH(ctx, k_dia_spmv_dot_p2p<ND>, (int)g, P2P_T, 0, ctx->dia, p, r, ap, n, part,      \
-           ticket, gin, a);                                                                 \
+    int64_t g = (hi0 + (n - lo1) + P2P_T - 1) / P2P_T;                                      \
+    if (g > (int64_t)8 * ctx->num_sms) g = (int64_t)8 * ctx->num_sms;                       \
+    if (g < 1) g = 1;                                                                       \
+    LAUNCH(ctx, k_dia_edges_p2p<ND>, (int)g, P2P_T, 0, ctx->dia, p, r, ap, n, hi0, lo1,     \
+           part, ticket, gin, a);                                                           \
   } break;
   switch (ctx->dia.nd) {
     P2P_CASE(1) P2P_CASE(2) P2P_CASE(3) P2P_CASE(4) P2P_CASE(5) P2P_CASE(6) P2P_CASE(7)

@@ -1264,6 +1264,39 @@ int b200_spmv_dots(b200_ctx* ctx, const double* w_owned, const double* rv_owned,
   return launch_spmv_dot(ctx, w_owned, rv_owned, out_owned, group);
 }
 
+// DIA operator: rows [hi0, lo1) only (the rows between the two halo-reading edges of a
+// slab); sums overwrite group[G_PAP..G_APAP].  p2p.cu adds the edges.
+int b200_spmv_dots_rows(b200_ctx* ctx, const double* p_owned, const double* r_owned,
+                        double* ap_owned, double* group, int64_t hi0, int64_t lo1) {
+  if (ctx->fmt != B200_FMT_DIA) FAIL(B200_ERR_ARG, "spmv_dots_rows: DIA operator only");
+  const int64_t n = ctx->n;
+  const int64_t rows = lo1 - hi0;
+  double* part = ctx->w_part.as<double>();
+  unsigned* ticket = ctx->w_ticket.as<unsigned>();
+  const double* dexp = ctx->dexp.as<double>();
+#define ROWS_CASE(ND)                                                                      \
+  case ND: {                                                                               \
+    static int occ = 0;                                                                    \
+    if (!occ) {                                                                            \
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dia_spmv_dot<ND, true>,     \
+                                                       PCG_T, 0));                         \
+      if (occ < 1) occ = 1;                                                                \
+    }                                                                                      \
+    int64_t g = (rows + PCG_T - 1) / PCG_T;                                                \
+    if (g > (int64_t)occ * ctx->num_sms) g = (int64_t)occ * ctx->num_sms;                  \
+    if (g < 1) g = 1;                                                                      \
+    LAUNCH(ctx, (k_dia_spmv_dot<ND, true>), (int)g, PCG_T, 0, ctx->dia, p_owned, r_owned,  \
+           dexp, ap_owned, n, hi0, lo1, n, 0, ctx->ka_chunk, part, ticket, group);         \
+  } break;
+  switch (ctx->dia.nd) {
+    ROWS_CASE(1) ROWS_CASE(2) ROWS_CASE(3) ROWS_CASE(4) ROWS_CASE(5) ROWS_CASE(6) ROWS_CASE(7)
+    ROWS_CASE(8) ROWS_CASE(9) ROWS_CASE(10) ROWS_CASE(11) ROWS_CASE(12) ROWS_CASE(13)
+    default: FAIL(B200_ERR_ARG, "bad diagonal count");
+  }
+#undef ROWS_CASE
+  return B200_OK;
+}
+
 int b200_apply_operator(b200_ctx* ctx, const double* w_owned, double* out_owned) {
   return launch_spmv_dot(ctx, w_owned, ctx->vr.as<double>() + ctx->pad, out_owned,
                          ctx->scal.as<double>() + SC_AUX0);

@@ -169,6 +169,18 @@ def spatial_order(coords, axis=0, blocks=64):
     return perm, inv
 
 
+def _runs(*cols):
+    """first index of every run of equal rows in the parallel integer arrays `cols`"""
+    n = cols[0].size
+    if n == 0:
+        return np.zeros(0, dtype=np.int64)
+    chg = np.zeros(n, dtype=bool)
+    chg[0] = True
+    for c in cols:
+        chg[1:] |= c[1:] != c[:-1]
+    return np.flatnonzero(chg)
+
+
 def join_slab_clusters(parts, Np):
     """Host half of the slab topology check.  parts[r] = (labels, has_bc, interior_bad)
     of rank r (b200_slab_clusters): labels / has-BC marks of the pores of rank r's two
@@ -176,23 +188,27 @@ def join_slab_clusters(parts, Np):
     region and rank r+1's low region are the same pores).  Two local clusters that
     label the same pore are one cluster; returns the number of clusters (complete ones
     + joined ones) that contain no BC pore -- what `is_fully_connected` tests
-    (openpnm/topotools/_topotools.py:993-1024).  Tiny: O(halo * ranks) integers."""
+    (openpnm/topotools/_topotools.py:993-1024).  The label arrays are run-length
+    compressed first (a healthy network is one run per region), so the graph that is
+    joined here has a handful of nodes."""
     import scipy.sparse as sprs
     from scipy.sparse import csgraph
     bad = int(sum(int(p[2]) for p in parts))
+    labs = [np.asarray(p[0]).astype(np.int64) for p in parts]
     keys, flags, ea, eb = [], [], [], []
-    for r, (lab, hb, _) in enumerate(parts):
-        lab = np.asarray(lab).astype(np.int64)
-        ok = lab >= 0
-        keys.append(r * np.int64(Np) + lab[ok])
-        flags.append(np.asarray(hb)[ok].astype(bool))
+    for r, lab in enumerate(labs):
+        hb = np.asarray(parts[r][1])
+        first = _runs(lab, hb)
+        first = first[lab[first] >= 0]
+        keys.append(r * np.int64(Np) + lab[first])
+        flags.append(hb[first].astype(bool))
         if r + 1 < len(parts):
             h2 = lab.size // 2
-            hi = lab[h2:]
-            lo = np.asarray(parts[r + 1][0]).astype(np.int64)[:h2]
-            both = (hi >= 0) & (lo >= 0)
-            ea.append(r * np.int64(Np) + hi[both])
-            eb.append((r + 1) * np.int64(Np) + lo[both])
+            hi, lo = lab[h2:], labs[r + 1][:h2]
+            f2 = _runs(hi, lo)
+            f2 = f2[(hi[f2] >= 0) & (lo[f2] >= 0)]
+            ea.append(r * np.int64(Np) + hi[f2])
+            eb.append((r + 1) * np.int64(Np) + lo[f2])
     keys = np.concatenate(keys) if keys else np.zeros(0, dtype=np.int64)
     if keys.size == 0:
         return bad
@@ -214,16 +230,28 @@ def join_slab_clusters(parts, Np):
 
 def slab_topology_check(ctx, conns_local, Np, row_begin, row_end, halo, bc_value, bc_rate):
     """`_validate_topology_health` of a slab run (collective): every rank labels the
-    clusters of the throats it holds on its GPU, the cut regions are joined on the
-    host.  Returns the number of clusters without a BC pore."""
+    clusters of the throats it holds on its GPU, the labels of the cut regions are
+    all-gathered (device tensors over NCCL) and joined on the host.  Returns the number
+    of clusters without a BC pore."""
+    import torch
     import torch.distributed as dist
     lab, hb, bad = ctx.slab_clusters(conns_local, Np, row_begin, row_end, halo, bc_value, bc_rate)
     ctx.synchronize()
-    part = (lab.cpu().numpy(), hb.cpu().numpy(), bad)
-    parts = [part]
-    if dist.is_initialized() and dist.get_world_size() > 1:
-        parts = [None] * dist.get_world_size()
-        dist.all_gather_object(parts, part)
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return join_slab_clusters([(lab.cpu().numpy(), hb.cpu().numpy(), bad)], Np)
+    world = dist.get_world_size()
+    on_dev = dist.get_backend() == "nccl"
+    mine = torch.cat([lab.to(torch.int32), hb.to(torch.int32),
+                      torch.tensor([bad], dtype=torch.int32, device=lab.device)])
+    if not on_dev:
+        mine = mine.cpu()
+    allp = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allp, mine)
+    n = lab.numel()
+    parts = []
+    for t in allp:
+        h = t.cpu().numpy()
+        parts.append((h[:n], h[n:2 * n].astype(np.uint8), int(h[2 * n])))
     return join_slab_clusters(parts, Np)
 
 

@@ -107,8 +107,9 @@ def main():
     from oracle import oracle
 
     rank, world, local = bdist.init_process_group()
+    small = "--skip-small" not in sys.argv
     # ---- 1: against the direct solve; the coarse levels are replicated at this size
-    for shape, fmt in (((48, 24, 24), "auto"), ((48, 24, 24), "csr")):
+    for shape, fmt in ((((48, 24, 24), "auto"), ((48, 24, 24), "csr")) if small else ()):
         Np, Nt, rb, re, ids, conns, g_all, bcv = lattice_case(bdist, oracle, shape, rank, world)
         net = oracle.cubic_network(shape)
         assert np.array_equal(conns, net["conns"][ids])
@@ -143,6 +144,8 @@ def main():
     # the slab Jacobi-PCG at rtol 1e-13 and the explicitly recomputed residual
     os.environ["B200_AMG_REPL"] = "64"
     try:
+        if not small:
+            raise StopIteration
         shape = (64, 40, 36)
         Np, Nt, rb, re, ids, conns, g_all, bcv = lattice_case(bdist, oracle, shape, rank, world, 5)
         ss = bdist.SlabSolver(Np, rb, re, device=local, fmt="auto")
@@ -168,6 +171,8 @@ def main():
                   f"jacobi={res['jacobi'][1]} it amg={res['amg'][1]} it levels={shape_of} "
                   f"max rel diff {dx:.1e}", flush=True)
         ss.ctx.close()
+    except StopIteration:
+        pass
     finally:
         del os.environ["B200_AMG_REPL"]
 
@@ -190,7 +195,10 @@ def main():
         bcv[Np - n * n:] = 1e5
         ss = bdist.SlabSolver(Np, rb, re, device=local, fmt="auto")
         res = {}
-        for precond in ("jacobi", "amg"):
+        if "--p2p" in sys.argv and world > 1:
+            ss.assemble(conns, g_loc, bcv, None)
+            ss.enable_p2p()
+        for precond in (("jacobi",) if "--jacobi-only" in sys.argv else ("jacobi", "amg")):
             ss.ctx.set_precond(precond)
             for rep in range(3):
                 ss.assemble(conns, g_loc, bcv, None)
@@ -203,6 +211,15 @@ def main():
                 dt = time.perf_counter() - t0
             assert info == 0, (precond, info, it, rel)
             res[precond] = (x_loc.clone(), it, dt, ss.ctx.stats())
+        if "--jacobi-only" in sys.argv:
+            if rank == 0:
+                sj = res["jacobi"][3]
+                print(f"dist jacobi-only Cubic {n}^3 world={world} p2p={'--p2p' in sys.argv} "
+                      f"order={os.environ.get('B200_P2P_ORDER', 'new')}: {res['jacobi'][1]} it "
+                      f"{res['jacobi'][2]*1e3:.1f} ms wall, device solve {sj['t_solve_ms']:.1f} ms "
+                      f"= {sj['t_solve_ms']/res['jacobi'][1]:.4f} ms/it", flush=True)
+            ss.ctx.close()
+            continue
         dx = float((res["amg"][0] - res["jacobi"][0]).abs().max() / res["jacobi"][0].abs().max())
         assert dx < 1e-5, dx          # both are rtol-1e-10 solutions of a kappa ~ 1e5 system
         if rank == 0:
