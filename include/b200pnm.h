@@ -319,6 +319,16 @@ int b200_rate_throats(b200_ctx* ctx, const int64_t* conns, const double* g,
                       const double* x, const int64_t* throats, int64_t k,
                       double* out);
 
+/* (Nt,2) conductance of AdvectionDiffusion: |g2[t][0] x[c1] - g2[t][1] x[c0]|          */
+int b200_rate_throats2(b200_ctx* ctx, const int64_t* conns, const double* g2,
+                       const double* x, const int64_t* throats, int64_t k,
+                       double* out);
+/* S1, S2 and rate of registered source number `index` at x for every owned pore
+ * (device, n each): what `regenerate_models` leaves on the phase after a run
+ * (_algorithm.py:89-91, source_terms/_funcs.py:61-69,108-116,158-168).        */
+int b200_source_values(b200_ctx* ctx, int index, const double* x, double* S1,
+                       double* S2, double* rate);
+
 /* ------------------------------------------------------------- statistics */
 typedef struct b200_stats {
   int64_t n, nnz_system, cg_iters;

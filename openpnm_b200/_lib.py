@@ -9,7 +9,9 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200pnm.so")
+# B200_LIB=dbg selects the bounds-checking build (python -m openpnm_b200.build --bounds)
+LIB_PATH = os.path.join(HERE, "libb200pnm_dbg.so" if os.environ.get("B200_LIB") == "dbg"
+                        else "libb200pnm.so")
 
 OK = 0
 ERR_NAMES = {-1: "CUDA", -2: "ARG", -3: "INDEX", -4: "NONFINITE", -5: "TOO_LARGE",
@@ -96,6 +98,8 @@ SIGNATURES = {
                                       _pi64, _pi64, _pi64, _pint]),
     "b200_rate_pores": (C.c_int, [_p, _p, _p, _i64, _p]),
     "b200_rate_throats": (C.c_int, [_p, _p, _p, _p, _p, _i64, _p]),
+    "b200_rate_throats2": (C.c_int, [_p, _p, _p, _p, _p, _i64, _p]),
+    "b200_source_values": (C.c_int, [_p, C.c_int, _p, _p, _p, _p]),
     "b200_get_stats": (C.c_int, [_p, C.POINTER(Stats)]),
     "b200_time_kernel": (C.c_int, [_p, C.c_int, C.c_int, _pdbl]),
     "b200_operator_bytes": (C.c_int, [_p, _pi64, _pi64]),

@@ -758,10 +758,10 @@ def _rate_slabs(self, x, pores, throats, mode):
     import torch.distributed as dist
     ss = self._slab
     if throats.size:
+        # every rank holds the full x on its device; the requested throats are named by
+        # their own conns / conductances (the context only knows the slab's throats)
         conns = np.asarray(self.network["throat.conns"], dtype=np.int64)[throats]
-        g = self._conductance()[throats]
-        xh = x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
-        R = np.abs(g * (xh[conns[:, 1]] - xh[conns[:, 0]]))      # trivial gather on the full x
+        R = ss.ctx.rate_throats_explicit(x, conns, self._conductance()[throats]).cpu().numpy()
         return np.array(np.sum(R) if mode == "group" else R, ndmin=1)
     out = torch.zeros(pores.size, dtype=torch.float64, device=ss.ctx.tdev)
     mine = np.flatnonzero((pores >= ss.row_begin) & (pores < ss.row_end))
@@ -1006,29 +1006,21 @@ class ReactiveTransport(Transport):
         except Exception:
             return
         iterative = self.iterative_props
-        for item in self["pore.source"].keys():
+        ctx, slab = self._ctx, getattr(self, "_slab", None)
+        slab = slab if (slab is not None and self._world_size() > 1) else None
+        # index = registration order on the context: run() registers the device-evaluated
+        # items in this order, the host hook re-registers ALL items in this order
+        for k, item in enumerate(self["pore.source"].keys()):
             if self._source_on_host(item, iterative):
                 continue            # regenerated on the phase by the update hook
-            name, m = self._model_of(item)
-            _, keys, defaults = _SRC_KINDS[name]
-            p = []
-            for k, d in zip(keys, defaults):
-                v = d if k is None else m.get(k, d)
-                if isinstance(v, str):
-                    v = np.asarray(self._phase[v], dtype=np.float64)
-                p.append(v)
-            with np.errstate(all="ignore"):
-                if name == "linear":
-                    S1, S2 = p[0] * np.ones_like(x), p[1] * np.ones_like(x)
-                    r = p[0] * x + p[1]
-                elif name == "power_law":
-                    r = p[0] * x ** p[1] + p[2]
-                    S1 = p[0] * p[1] * x ** (p[1] - 1)
-                    S2 = p[0] * x ** p[1] * (1 - p[1]) + p[2]
-                else:
-                    r = p[0] * x ** p[1]
-                    S1 = p[0] * p[1] * x ** (p[1] - 1)
-                    S2 = p[0] * (1 - p[1]) * x ** p[1]
+            # S1 / S2 / rate at the converged x from the device kernel that linearised
+            # them during the run (b200_source_values), not re-derived in numpy
+            if slab is not None:
+                xl = self._x_dev[slab.row_begin:slab.row_end]
+                vals = [slab.gather(v) for v in ctx.source_values(k, xl)]
+            else:
+                vals = ctx.source_values(k, self._x_dev)
+            S1, S2, r = (v.cpu().numpy() for v in vals)
             try:
                 self._phase[f"pore.{item}.S1"] = S1
                 self._phase[f"pore.{item}.S2"] = S2
@@ -1104,9 +1096,11 @@ class AdvectionDiffusion(ReactiveTransport):
             # |g[:,0] x[c1] - g[:,1] x[c0]| (_transport.py:306-319 with the flipped (Nt,2) g)
             if self._parse_indices(pores).size:
                 raise Exception("Must specify either pores or throats, not both")
+            if self._ctx is None:
+                raise Exception("run() first")
             c = np.asarray(self.network["throat.conns"])[throats_i]
-            x = np.asarray(self.x)
-            R = np.abs(g[throats_i, 0] * x[c[:, 1]] - g[throats_i, 1] * x[c[:, 0]])
+            x = self._x_dev if self._x_dev is not None else self.x
+            R = self._ctx.rate_throats_explicit(x, c, g[throats_i]).cpu().numpy()
             return np.array(np.sum(R) if mode == "group" else R, ndmin=1)
         return super().rate(pores=pores, throats=throats, mode=mode)
 

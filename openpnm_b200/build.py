@@ -42,17 +42,27 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
+LIB_DBG = os.path.join(HERE, "libb200pnm_dbg.so")
+
+
+def build_library(force=False, verbose=False, bounds=False):
+    """bounds=True: the debug build with in-kernel index asserts (-DB200_BOUNDS), written to
+    libb200pnm_dbg.so and loaded instead of the normal library when B200_LIB=dbg."""
+    if bounds:
+        return _build(LIB_DBG, os.path.join(HERE, "build", "dbg"), verbose, ["-DB200_BOUNDS"])
     if not force and not needs_build():
         return LIB
+    return _build(LIB, os.path.join(HERE, "build"), verbose, [])
+
+
+def _build(LIB, objdir, verbose, extra):
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
     ni = _nccl_include()
     if ni and ni != "/usr/include":
         inc += ["-I", ni]
-    flags = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"] + ARCH
+    flags = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"] + ARCH + extra
     if verbose:
         flags += ["-Xptxas", "-v"]
     procs, objs = [], []
@@ -77,4 +87,5 @@ def build_library(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv,
+                        bounds="--bounds" in sys.argv))

@@ -300,7 +300,11 @@ __global__ void __launch_bounds__(AMG_T) k_amg_fill_members(int n, const int* __
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int a = agg[i];
-    if (a >= 0) cmem[cptr[a] + atomicAdd(&cur[a], 1)] = i;
+    if (a >= 0) {
+      const int slot = atomicAdd(&cur[a], 1);
+      B200_ASSERT(cptr[a] + slot < cptr[a + 1]);
+      cmem[cptr[a] + slot] = i;
+    }
   }
 }
 
@@ -370,6 +374,7 @@ __global__ void __launch_bounds__(128) k_amg_row_build(int nc, const int* __rest
         int a = agg[j];           // slab runs: global coarse id (halo entries included)
         if (a < 0) continue;
         a -= coff;                // -> local signed id: < 0 rank-1's rows, >= nc rank+1's
+        B200_ASSERT(m <= AMG_ROWCAP || spilled);
         const double v = (diag != nullptr && j == i) ? diag[i] : av[e];
         int k = 0;
         if (!spilled) {
@@ -582,6 +587,7 @@ __global__ void __launch_bounds__(AMG_T) k_amg_restrict(int nc, const int* __res
     double s = 0.0;
     for (int m = cptr[I]; m < cptr[I + 1]; ++m) {
       const int i = cmem[m];
+      B200_ASSERT(i >= 0);
       const double r = ax ? b[i] - ax[i] : b[i];
       s += w ? w[i] * r : r;
     }
@@ -596,6 +602,7 @@ __global__ void __launch_bounds__(AMG_T) k_amg_prolong(int64_t n, const int* __r
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int a = agg[i];
+    B200_ASSERT(a >= -1);
     if (a >= 0) x[i] += w ? w[i] * ec[a] : ec[a];
   }
 }

@@ -207,11 +207,13 @@ __global__ void k_fill_conns(ConnsSrc src, int64_t rb, int64_t re,
     if (c.x >= rb && c.x < re) {
       int r = (int)(c.x - rb);
       int slot = atomicSub(&cursor[r], 1) - 1;
+      B200_ASSERT(slot >= 0 && rowofs[r] + slot < rowofs[r + 1]);
       keys[(int64_t)rowofs[r] + slot] = ((unsigned long long)c.y << 32) | (unsigned)t;
     }
     if (c.y >= rb && c.y < re) {
       int r = (int)(c.y - rb);
       int slot = atomicSub(&cursor[r], 1) - 1;
+      B200_ASSERT(slot >= 0 && rowofs[r] + slot < rowofs[r + 1]);
       // bit 31 of the low word marks the (c1 -> c0) direction of the throat
       keys[(int64_t)rowofs[r] + slot] =
           ((unsigned long long)c.x << 32) | (unsigned)t | 0x80000000u;

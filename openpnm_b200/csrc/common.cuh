@@ -10,6 +10,17 @@
 
 #include "b200pnm.h"
 
+// Debug build (python -m openpnm_b200.build --bounds -> libb200pnm_dbg.so, selected with
+// B200_LIB=dbg): in-kernel index checks on the gathers and scatters of the hot kernels.
+// compute-sanitizer is not available on the GPU pool, so the small golden tests are run
+// under this build instead (profiles/README.md).
+#ifdef B200_BOUNDS
+#include <assert.h>
+#define B200_ASSERT(c) assert(c)
+#else
+#define B200_ASSERT(c) ((void)0)
+#endif
+
 #define B200_MAX_SRC 8
 #define B200_MAX_DIAGS 13     // Cubic(connectivity=26) has 13 super-diagonals
 

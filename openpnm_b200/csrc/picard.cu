@@ -259,3 +259,69 @@ extern "C" int b200_rate_throats(b200_ctx* ctx, const int64_t* conns, const doub
   CK(cudaStreamSynchronize(ctx->stream));
   return B200_OK;
 }
+
+
+// Two-way (Nt,2) conductance (AdvectionDiffusion): |g[t][0] x[c1] - g[t][1] x[c0]|
+// (_transport.py:306-319 with the flipped (Nt,2) g of network/_network.py:281-285)
+__global__ void k_rate_throats2(const longlong2* __restrict__ conns, const double* __restrict__ g2,
+                                const double* __restrict__ x, const long long* __restrict__ throats,
+                                int64_t k, double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < k; q += stride) {
+    const long long t = throats[q];
+    const longlong2 c = conns[t];
+    // two rounded products, then the difference -- as numpy evaluates it; a fused
+    // multiply-add would round differently where the two fluxes nearly cancel
+    out[q] = fabs(__dsub_rn(__dmul_rn(g2[2 * t], x[c.y]), __dmul_rn(g2[2 * t + 1], x[c.x])));
+  }
+}
+
+extern "C" int b200_rate_throats2(b200_ctx* ctx, const int64_t* conns, const double* g2,
+                                  const double* x, const int64_t* throats, int64_t k, double* out) {
+  if (!ctx) return B200_ERR_ARG;
+  if (k <= 0) return B200_OK;
+  LAUNCH(ctx, k_rate_throats2, grid_for(k, 256), 256, 0,
+         reinterpret_cast<const longlong2*>(conns), g2, x,
+         reinterpret_cast<const long long*>(throats), k, out);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+// S1, S2 and the rate r of one registered source term at x, for the masked pores (0
+// elsewhere): what `regenerate_models` leaves on the phase after the run
+// (_algorithm.py:89-91; source_terms/_funcs.py:61-69,108-116,158-168).
+__global__ void k_source_values(SrcTerm s, const double* __restrict__ x, int64_t n,
+                                double* __restrict__ S1o, double* __restrict__ S2o,
+                                double* __restrict__ ro) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double X = x[i], p1 = s.p1[i], p2 = s.p2[i], p3 = s.p3 ? s.p3[i] : 0.0;
+    double S1, S2, r;
+    if (s.kind == B200_SRC_LINEAR) {
+      S1 = p1; S2 = p2; r = p1 * X + p2;
+    } else if (s.kind == B200_SRC_POWER_LAW) {
+      const double xb = pow(X, p2);
+      r = p1 * xb + p3;
+      S1 = p1 * p2 * pow(X, p2 - 1.0);
+      S2 = p1 * xb * (1.0 - p2) + p3;
+    } else {
+      const double xb = pow(X, p2);
+      r = p1 * xb;
+      S1 = p1 * p2 * pow(X, p2 - 1.0);
+      S2 = p1 * (1.0 - p2) * xb;
+    }
+    S1o[i] = S1; S2o[i] = S2; ro[i] = r;
+  }
+}
+
+extern "C" int b200_source_values(b200_ctx* ctx, int index, const double* x, double* S1,
+                                  double* S2, double* rate) {
+  if (!ctx || !x || !S1 || !S2 || !rate) return B200_ERR_ARG;
+  if (index < 0 || index >= ctx->srcs.n) FAIL(B200_ERR_ARG, "source_values: no such source");
+  LAUNCH(ctx, k_source_values, grid_for(ctx->n, 256), 256, 0, ctx->srcs.s[index], x, ctx->n, S1, S2,
+         rate);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}

@@ -358,6 +358,7 @@ __global__ void k_offdiag_emit(const int* __restrict__ indptr, const int* __rest
       const int64_t j = indices[e];
       if (j == gi) continue;
       const int64_t lj = j - rb;
+      B200_ASSERT(o < optr[r + 1]);
       ocols[o] = (int)lj;
       ovals[o] = data[e] * sr * s_owned[lj];
       ++o;
@@ -437,6 +438,7 @@ __global__ void __launch_bounds__(256) k_sell_fill(const int* __restrict__ optr,
     const int self = r >= 0 ? r : 0;
     for (int k = 0; k < width; ++k) {
       const bool in = k < len;
+      B200_ASSERT(b + k * SELL_C + lane < sptr[nslices]);
       scols[b + k * SELL_C + lane] = in ? ocols[e0 + k] : self;
       svals[b + k * SELL_C + lane] = in ? ovals[e0 + k] : 0.0;
     }
@@ -856,6 +858,7 @@ __global__ void __launch_bounds__(T, (UNR >= 16 ? 2 : UNR >= 8 ? 4 : 5) * (256 /
     __syncthreads();
     const int ilo = (int)lo;
 #define SELL_GET(cc) (((unsigned)((cc) - ilo) < (unsigned)(SELL_SIGMA + 2 * W)) ? pw[(cc) - ilo] : p[cc])
+#define SELL_CHECK(cc) B200_ASSERT((cc) >= -pad && (cc) < n + pad)
     for (int sl = warp; sl < SPW; sl += NW) {
       const int64_t s = win * SPW + sl;
       const int b = sptr[s], width = (sptr[s + 1] - b) >> 5;
@@ -875,7 +878,7 @@ __global__ void __launch_bounds__(T, (UNR >= 16 ? 2 : UNR >= 8 ? 4 : 5) * (256 /
         double vv[T];                                                         \
         _Pragma("unroll") for (int u = 0; u < (T); ++u) cc[u] = c[(k + u) * SELL_C];   \
         _Pragma("unroll") for (int u = 0; u < (T); ++u) vv[u] = v[(k + u) * SELL_C];   \
-        _Pragma("unroll") for (int u = 0; u < (T); ++u) a[u] += vv[u] * SELL_GET(cc[u]); \
+        _Pragma("unroll") for (int u = 0; u < (T); ++u) { SELL_CHECK(cc[u]); a[u] += vv[u] * SELL_GET(cc[u]); } \
       }
       SELL_TIER(UNR)
       if (UNR > 4) { SELL_TIER(4) }
@@ -884,9 +887,11 @@ __global__ void __launch_bounds__(T, (UNR >= 16 ? 2 : UNR >= 8 ? 4 : 5) * (256 /
       double tot = 0.0;
 #pragma unroll
       for (int u = UNR - 1; u >= 0; --u) tot += a[u];
+      B200_ASSERT(r < 0 || (r >= r0 && r < r0 + SELL_SIGMA && r < n));
       if (r >= 0) accw[r - r0] = tot;
     }
 #undef SELL_GET
+#undef SELL_CHECK
     __syncthreads();
     for (int i = threadIdx.x; i < SELL_SIGMA; i += T) {
       const int64_t r = r0 + i;

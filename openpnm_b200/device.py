@@ -501,6 +501,32 @@ class Context:
                                             self._p(throats), int(throats.numel()), self._p(out)))
         return self._publish(out)
 
+    def rate_throats_explicit(self, x, conns_sel, g_sel):
+        """|g (x[c1] - x[c0])| (g (k,)) or |g0 x[c1] - g1 x[c0]| (g (k,2)) for an explicit
+        list of throats given by their conns and conductances (slab runs, where the context
+        holds the rank's throats only; AdvectionDiffusion's two-way conductance)."""
+        torch = _torch()
+        x = self.to_device(x, torch.float64)
+        conns = self.to_device(np.ascontiguousarray(conns_sel, dtype=np.int64), torch.int64)
+        g = np.ascontiguousarray(g_sel, dtype=np.float64)
+        k = int(conns.numel() // 2)
+        gd = self.to_device(g.reshape(-1), torch.float64)
+        idx = self.to_device(np.arange(k, dtype=np.int64), torch.int64)
+        out = self.empty(k, torch.float64)
+        fn = self.lib.b200_rate_throats2 if g.ndim == 2 else self.lib.b200_rate_throats
+        self._ck(fn(self._h, self._p(conns), self._p(gd), self._p(x), self._p(idx), k,
+                    self._p(out)))
+        return self._publish(out)
+
+    def source_values(self, index, x):
+        """(S1, S2, rate) device tensors of registered source number `index` at x"""
+        torch = _torch()
+        x = self.to_device(x, torch.float64)
+        S1, S2, r = (self.empty(self.n, torch.float64) for _ in range(3))
+        self._ck(self.lib.b200_source_values(self._h, int(index), self._p(x), self._p(S1),
+                                             self._p(S2), self._p(r)))
+        return self._publish(S1, S2, r)
+
     def time_kernel(self, which, reps=20):
         ms = C.c_double()
         self._ck(self.lib.b200_time_kernel(self._h, int(which), int(reps), C.byref(ms)))
