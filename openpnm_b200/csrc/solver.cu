@@ -703,6 +703,8 @@ __global__ void __launch_bounds__(PCG_T) k_dia_spmv_dot(DiaPack A, const double*
 //   mode 3  next step from x = p:    dd = c1 d + c2 (b - y),   d = dd, out = p + dd,
 //             and sum aux[i] out[i] (aux may be null)
 //   mode 4  weighted residual:       out = aux[i] (b - y)
+// (an fp32 copy of the diagonals for this kernel was tried: 301 instead of 278 ms per solve at
+// 400^3 -- slower, the kernel is not limited by those bytes -- and dropped)
 template <int ND>
 __global__ void __launch_bounds__(PCG_T) k_dia_smooth(DiaPack A, int mode,
                                                       const double* __restrict__ p,

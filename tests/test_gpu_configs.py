@@ -98,6 +98,42 @@ def test_config5_reactive_power_law_on_device(b2):
     assert abs(q_in + consumed) <= 1e-5 * abs(q_in)
 
 
+def test_config5_at_the_stated_size(b2):
+    """BASELINE config 5 at its stated size: Cubic 200^3 (8 M pores) ReactiveTransport with the
+    power-law sink, Picard loop on the device, with the multigrid and with Jacobi inside the
+    loop: same outer iterations, same x; size-independent properties (mass balance,
+    r = S1 c + S2, maximum principle)."""
+    n = 200
+    pn = b2.Cubic([n, n, n], coords=False)
+    g = hetero(pn.Nt)
+    left = pn.pores("left")
+    free = np.setdiff1d(pn.Ps, left)
+    out = {}
+    for precond in ("amg", "jacobi"):
+        ph = b2.Phase(pn)
+        dict.__setitem__(ph, "throat.diffusive_conductance", g)
+        ph["pore.A1"], ph["pore.A2"], ph["pore.A3"] = -1e-13, 2.0, 0.0
+        ph.add_model(propname="pore.rxn", model="power_law", X="pore.concentration",
+                     A1="pore.A1", A2="pore.A2", A3="pore.A3")
+        rt = b2.ReactiveTransport(network=pn, phase=ph)
+        rt.settings._update({"quantity": "pore.concentration",
+                             "conductance": "throat.diffusive_conductance"})
+        rt.set_value_BC(pores=left, values=1.0)
+        rt.set_source(pores=free, propname="pore.rxn")
+        rt.run(solver=b2.B200PCG(tol=1e-10, precond=precond))
+        assert rt.soln.is_converged
+        c = rt.x
+        assert c.min() >= -1e-9 and c.max() <= 1 + 1e-9
+        S1, S2, r = (ph[f"pore.rxn.{k}"] for k in ("S1", "S2", "rate"))
+        np.testing.assert_allclose(r, S1 * c + S2, rtol=1e-9, atol=1e-30)
+        q_in = rt.rate(pores=left)[0]
+        assert abs(q_in + r[free].sum()) <= 1e-5 * abs(q_in)
+        out[precond] = (np.array(c), rt.soln.num_iter, rt.soln.cg_iters)
+    assert out["amg"][1] == out["jacobi"][1]
+    assert np.max(np.abs(out["amg"][0] - out["jacobi"][0])) <= 1e-6
+    assert out["amg"][2] < out["jacobi"][2] / 4
+
+
 def test_config4_irregular_delaunay_sorted(b2):
     """Delaunay network (irregular coordination), isolated pores trimmed, pores
     renumbered by x: exercises the CSR-stream operator at 150k pores and is checked
