@@ -302,7 +302,10 @@ int b200_conductance_values(b200_ctx* ctx, double* g_out);
  * within [t0, t1]) are the output times (t_eval); nsave = 0 stores every
  * accepted step like t_eval=None.  out: device, `capacity` rows of n;
  * times_h: host, `capacity` doubles.  status: 0 finished, -1 step size too
- * small, -2 capacity exhausted.                                             */
+ * small, -2 capacity exhausted.  Slab runs (b200_comm_init): x0, volume and
+ * out hold the rank's rows; the halo of every right-hand side's operand is
+ * exchanged and the controller's norms are all-reduced, so all ranks take the
+ * same steps (symmetric systems; collective).                                */
 int b200_transient_rk45(b200_ctx* ctx, const double* x0, const double* volume,
                         double t0, double t1, double rtol, double atol,
                         const double* saveat_h, int64_t nsave, int64_t capacity,

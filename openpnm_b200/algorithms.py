@@ -1143,6 +1143,8 @@ class TransientReactiveTransport(ReactiveTransport):
             raise NotImplementedError("transient runs need device-evaluated models "
                                       "(linear, power_law, standard_kinetics sources; "
                                       "constant conductance)")
+        if self._world_size() > 1 and getattr(integrator, "distributed", True):
+            return self._run_transient_slabs(integrator, x0, V, tspan, saveat)
         try:
             self._assemble(ctx)
             ctx.clear_sources()
@@ -1171,6 +1173,77 @@ class TransientReactiveTransport(ReactiveTransport):
             self._x_dev = Y[-1]
         self.stats = ctx.stats()
         self._post_run(self[q])
+
+
+def _run_transient_slabs(self, integrator, x0, V, tspan, saveat):
+    """The transient run under torchrun: slabs of the index-ordered pores as in
+    `Transport._run_slabs`; `b200_transient_rk45` exchanges the halo of every right-hand
+    side's operand and all-reduces the step controller's norms, so every rank takes the same
+    steps; the saved states are gathered and every rank ends with the full solution."""
+    import torch
+    import torch.distributed as dist
+    from . import dist as bdist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    g = self._conductance()
+    if g.ndim != 1:
+        raise NotImplementedError("TransientAdvectionDiffusion is not slab-parallel: pass "
+                                  "B200RK45(distributed=False)")
+    rb, re, band, sel, conns_loc = self._slab_plan(world, rank)
+    key = (id(self.network), world, rank, integrator.device, integrator.fmt)
+    ss = getattr(integrator, "_slab", None)
+    if ss is None or getattr(integrator, "_slab_key", None) != key:
+        ss = bdist.SlabSolver(self.Np, rb, re, device=integrator.device, fmt=integrator.fmt)
+        integrator._slab, integrator._slab_key = ss, key
+    ctx = ss.ctx
+    self._ctx, self._slab = ctx, ss
+    conns_dev = ctx.to_device(conns_loc, torch.int64)
+    bv_dev = self._slab_bc_dev(ctx, "pore.bc.value", rb, re, band)
+    br_dev = self._slab_bc_dev(ctx, "pore.bc.rate", rb, re, band)
+    if self.settings["validate_topology"]:
+        if bdist.slab_topology_check(ctx, conns_dev, self.Np, rb, re, band, bv_dev, br_dev):
+            raise Exception("Your network is clustered, making Ax = b ill-conditioned")
+    q = self.settings["quantity"]
+    try:
+        srcs = self._sources()
+        ss.assemble(conns_dev, self._slab_take(ctx, g, sel), bv_dev, br_dev,
+                    keep_zero_diag=len(srcs) > 0)
+        self._slab_cache_key = None
+        ctx.clear_sources()
+        for smask, kind, p1, p2, p3 in srcs:
+            loc = [None if p is None else
+                   (p[rb:re] if np.ndim(p) else np.full(re - rb, float(p))) for p in (p1, p2, p3)]
+            ctx.add_source(kind, smask[rb:re], *loc)
+        cap = None
+        if saveat is None:
+            cap = integrator.max_saved or max(16, min(20000, int(2e9 // (8 * (re - rb)))))
+        t, Y, nsteps, nfev, status = ctx.transient_rk45(
+            x0[rb:re], V[rb:re], float(tspan[0]), float(tspan[1]), rtol=integrator.rtol,
+            atol=integrator.atol, saveat=saveat, capacity=cap)
+    except _lib.B200Error as e:
+        if e.code == -4:
+            raise Exception("A or b contains inf/nan values") from e
+        raise
+    if status == -1:
+        raise Exception("Required step size is less than spacing between numbers.")
+    if status == -2:
+        raise Exception("too many accepted steps to store them all: pass `saveat`")
+    nout = int(Y.shape[0])
+    with torch.cuda.stream(ctx.stream):
+        mine = Y.T.contiguous().reshape(-1)                  # (n_local, nout), row-major
+    Yfull = ss.gather(mine).reshape(self.Np, nout)           # rank blocks stack along the pores
+    Yh = Yfull.cpu().numpy()
+    self.soln = SolutionContainer()
+    self.soln[q] = TransientSolution(t, Yh)
+    self.soln.nsteps, self.soln.nfev = int(nsteps), int(nfev)
+    if nout:
+        dict.__setitem__(self, q, Yh[:, -1].copy())
+        with torch.cuda.stream(ctx.stream):
+            self._x_dev = Yfull[:, -1].contiguous()
+    self.stats = ctx.stats()
+    self._post_run(self[q])
+
+
+TransientReactiveTransport._run_transient_slabs = _run_transient_slabs
 
 
 class TransientFickianDiffusion(TransientReactiveTransport):

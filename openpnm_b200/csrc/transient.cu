@@ -199,6 +199,7 @@ struct Tr {
     double* w = ctx->vp.as<double>() + pad;
     double* aw = ctx->vap.as<double>() + pad;
     LAUNCH(ctx, k_tr_prescale, g, TR_T, 0, y, s, w, n);
+    RET(b200_halo_exchange(ctx, ctx->vp.as<double>()));     // slab run: the neighbours' edge rows
     RET(b200_apply_operator(ctx, w, aw));
     LAUNCH(ctx, k_tr_rhs, g, TR_T, 0, aw, s, b0, y, vol, srcs, f, n, ctx->w_flags.as<int>());
     ++nfev;
@@ -214,7 +215,9 @@ extern "C" int b200_transient_rk45(b200_ctx* ctx, const double* x0, const double
                                    int64_t* nsteps, int64_t* nfev, int* status) {
   if (!ctx || !ctx->have_sys || !x0 || !volume || !out || !times_h || !nout || capacity < 1)
     return B200_ERR_ARG;
-  if (ctx->nranks > 1) FAIL(B200_ERR_ARG, "transient: single GPU only");
+  // slab run (one rank per GPU): every right-hand side exchanges the halo of its operand,
+  // the step controller's norms are all-reduced, so every rank takes the same steps
+  const bool multi = ctx->nranks > 1;
   if (!(t1 > t0)) FAIL(B200_ERR_ARG, "transient: tspan must be increasing");
   CK(cudaSetDevice(ctx->device));
   const int64_t n = ctx->n;
@@ -275,13 +278,14 @@ extern "C" int b200_transient_rk45(b200_ctx* ctx, const double* x0, const double
   CKT(cudaMemcpyAsync(y, x0, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   TRY(tr.rhs(y, Kbuf[0]));                       // self.f = fun(t0, y0)
   double t = t0;
-  const double sqn = sqrt((double)n);
+  const double sqn = sqrt((double)(multi ? ctx->n_global : n));
 
   // ---- select_initial_step (scipy/integrate/_ivp/common.py)
   double h_abs;
   {
     LAUNCH(ctx, k_tr_norms, g, TR_T, 0, y, y, Kbuf[0], (const double*)nullptr, rtol, atol, n, part,
            ticket, sc + SC_AUX0);
+    TRY(b200_allreduce_sum(ctx, sc + SC_AUX0, 3));
     CKT(cudaMemcpyAsync(ctx->scal_h + SC_AUX0, sc + SC_AUX0, 3 * sizeof(double),
                         cudaMemcpyDeviceToHost, ctx->stream));
     CKT(cudaStreamSynchronize(ctx->stream));
@@ -295,6 +299,7 @@ extern "C" int b200_transient_rk45(b200_ctx* ctx, const double* x0, const double
     TRY(tr.rhs(ystage, Kbuf[1]));
     LAUNCH(ctx, k_tr_norms, g, TR_T, 0, y, y, Kbuf[0], Kbuf[1], rtol, atol, n, part, ticket,
            sc + SC_AUX0);
+    TRY(b200_allreduce_sum(ctx, sc + SC_AUX0, 3));
     CKT(cudaMemcpyAsync(ctx->scal_h + SC_AUX0, sc + SC_AUX0, 3 * sizeof(double),
                         cudaMemcpyDeviceToHost, ctx->stream));
     CKT(cudaStreamSynchronize(ctx->stream));
@@ -339,12 +344,14 @@ extern "C" int b200_transient_rk45(b200_ctx* ctx, const double* x0, const double
       TRY(tr.rhs(ynew, Kbuf[6]));
       LAUNCH(ctx, k_tr_error, g, TR_T, 0, y, ynew, h, E, K, rtol, atol, n, part, ticket,
              sc + SC_AUX0);
+      TRY(b200_allreduce_sum(ctx, sc + SC_AUX0, 1));
       CKT(cudaMemcpyAsync(ctx->scal_h + SC_AUX0, sc + SC_AUX0, sizeof(double),
                           cudaMemcpyDeviceToHost, ctx->stream));
       CKT(cudaMemcpyAsync(ctx->flags_h, ctx->w_flags.p, FLAG_COUNT * sizeof(int),
                           cudaMemcpyDeviceToHost, ctx->stream));
       CKT(cudaStreamSynchronize(ctx->stream));
-      if (ctx->flags_h[FLAG_NONFINITE]) {
+      // (slab run: a rank-local inf/nan makes the all-reduced norm non-finite on every rank)
+      if ((!multi && ctx->flags_h[FLAG_NONFINITE]) || !isfinite(ctx->scal_h[SC_AUX0])) {
         ctx->err = "transient: the right-hand side produced inf/nan";
         return fail(B200_ERR_NONFINITE);
       }

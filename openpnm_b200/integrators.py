@@ -14,7 +14,9 @@ class Integrator:
 
 
 class B200RK45(Integrator):
-    """Explicit Runge-Kutta 5(4) time stepping on one B200.
+    """Explicit Runge-Kutta 5(4) time stepping on one B200 -- or, under torchrun, on the
+    slabs of all ranks (every right-hand side exchanges the halo of its operand, the step
+    controller's error norms are all-reduced, so all ranks take the same steps).
 
     Parameters mirror `ScipyRK45`: ``atol``, ``rtol`` (defaults 1e-6).  The
     transient algorithms of `openpnm_b200.algorithms` hand it their assembled
@@ -23,7 +25,12 @@ class B200RK45(Integrator):
 
     _b200_native = True
 
-    def __init__(self, atol=1e-6, rtol=1e-6, verbose=False, device=0, fmt="auto", max_saved=None):
+    def __init__(self, atol=1e-6, rtol=1e-6, verbose=False, device=None, fmt="auto", max_saved=None,
+                 distributed=True):
+        if device is None:          # under torchrun: one process per GPU
+            import os
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.distributed = distributed   # slab-parallel run() when torch.distributed is up
         self.atol = atol
         self.rtol = rtol
         self.verbose = verbose

@@ -202,6 +202,42 @@ def main():
     if rank == 0:
         print(f"dist ok delaunay Np={pn3.Np} Nt={pn3.Nt} band={bdist.bandwidth(pn3.conns)} "
               f"world={world} iters={its} fmt={fd._ctx.pcg_format()}", flush=True)
+    # ---- transient run, slab-parallel (RK45 on the device: halo exchange per right-hand
+    # side, all-reduced error norms): same accepted steps and states as scipy's RK45
+    shape = (16, 10, 8)
+    pnt = b2.Cubic(shape, spacing=1e-4, coords=False)
+    rng = np.random.default_rng(3)
+    gt = 10.0 ** rng.uniform(-15, -14, pnt.Nt)
+    V = rng.uniform(0.5, 1.5, pnt.Np) * 1e-12
+    pnt["pore.volume"] = V
+    pht = b2.Phase(pnt)
+    pht["throat.diffusive_conductance"] = gt
+    pht["pore.A1"], pht["pore.A2"], pht["pore.A3"] = -2e-15, 1.5, 0.0
+    pht.add_model(propname="pore.rxn", model="power_law", X="pore.concentration",
+                  A1="pore.A1", A2="pore.A2", A3="pore.A3")
+    for with_source in (False, True):
+        alg = b2.TransientFickianDiffusion(network=pnt, phase=pht)
+        alg.set_value_BC(pores=pnt.pores("left"), values=1.0)
+        alg.set_rate_BC(pores=pnt.pores("right")[:20], rates=-1e-16)
+        srcs = ()
+        if with_source:
+            sp = np.setdiff1d(pnt.Ps, np.union1d(pnt.pores("left"), pnt.pores("right")))
+            alg.set_source(pores=sp, propname="pore.rxn")
+            sm = np.zeros(pnt.Np, dtype=bool)
+            sm[sp] = True
+            srcs = [(sm, "power_law", {"A1": -2e-15, "A2": 1.5, "A3": 0.0})]
+        alg.run(x0=0.1, tspan=(0, 300.0), integrator=b2.B200RK45(atol=1e-9, rtol=1e-7))
+        sol = alg.soln["pore.concentration"]
+        t_o, Y_o = oracle.transient_run(pnt.conns, gt, pnt.Np, V, 0.1, (0, 300.0),
+                                        bc_value=alg["pore.bc.value"], bc_rate=alg["pore.bc.rate"],
+                                        sources=srcs, rtol=1e-7, atol=1e-9)
+        assert sol.t.size == t_o.size, (sol.t.size, t_o.size)      # same accepted steps
+        np.testing.assert_allclose(sol.t, t_o, rtol=1e-9)
+        assert np.max(np.abs(np.asarray(sol) - Y_o)) <= 1e-9
+        assert np.array_equal(alg.x, np.asarray(sol)[:, -1])
+    if rank == 0:
+        print(f"dist ok transient world={world} steps={alg.soln.nsteps} nfev={alg.soln.nfev}",
+              flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
