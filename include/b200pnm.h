@@ -89,12 +89,16 @@ int b200_build_laplacian(b200_ctx* ctx, const int64_t* conns, const double* g,
  * (openpnm/algorithms/_advection_diffusion.py:43-105; (Nt,2) weights,
  * network/_network.py:281-285): g2 is (Nt,2) row-major, entry (c0,c1) carries
  * g2[t][0], entry (c1,c0) carries g2[t][1]; the diagonal is the column sum as
- * in scipy's in-degree Laplacian.  Whole network only.  Systems built from it
- * are solved by Jacobi-scaled BiCGStab inside b200_pcg / b200_picard.
+ * in scipy's in-degree Laplacian.  Systems built from it are solved by
+ * Jacobi-scaled BiCGStab inside b200_pcg / b200_picard (slab runs included).
  * b200_add_to_diagonal adds the outflow BC values (NaN = none) to the system
  * diagonal after b200_apply_bcs(keep_zero_diag = 1).                        */
 int b200_build_laplacian2(b200_ctx* ctx, const int64_t* conns, const double* g2,
                           int64_t Np, int64_t Nt, int64_t* nnz);
+/* rows [row_begin,row_end) only, from the throats touching them (slab runs)  */
+int b200_build_laplacian2_rows(b200_ctx* ctx, const int64_t* conns,
+                               const double* g2, int64_t Np, int64_t Nt,
+                               int64_t row_begin, int64_t row_end, int64_t* nnz);
 int b200_add_to_diagonal(b200_ctx* ctx, const double* add);
 
 /* ------------------------------------------------- topology health check

@@ -58,6 +58,7 @@ SIGNATURES = {
     "b200_synchronize": (C.c_int, [_p]),
     "b200_build_laplacian": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _pi64]),
     "b200_build_laplacian2": (C.c_int, [_p, _p, _p, _i64, _i64, _pi64]),
+    "b200_build_laplacian2_rows": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _pi64]),
     "b200_add_to_diagonal": (C.c_int, [_p, _p]),
     "b200_check_topology": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _pi64, _pi64]),
     "b200_cluster_labels": (C.c_int, [_p, _p, _i64, _i64, _p, _pi64]),

@@ -586,7 +586,9 @@ class Transport(dict):
             srcs = self._sources()
             f, nnz0, nnz = ss.assemble(conns_dev, None if reuse else self._slab_take(ctx, g, sel),
                                        bv_dev, br_dev,
-                                       keep_zero_diag=len(srcs) > 0, reuse_laplacian=reuse)
+                                       keep_zero_diag=len(srcs) > 0 or self._slab_keep_diag(),
+                                       reuse_laplacian=reuse)
+            self._slab_after_assemble(ctx)
             self._slab_cache_key = ckey
             st.mark("upload g+assemble")
             ctx.clear_sources()
@@ -667,6 +669,12 @@ class Transport(dict):
         self._slab_plan_cache = (key, out)
         return out
 
+    def _slab_keep_diag(self):
+        return False
+
+    def _slab_after_assemble(self, ctx):
+        pass
+
     def _slab_bc_dev(self, ctx, key, rb, re, band):
         """Global-length BC array on this rank's device of which only the part the rank
         reads -- its rows and the halo columns, [rb - band, re + band) -- is uploaded;
@@ -692,6 +700,8 @@ class Transport(dict):
         import torch
         if not isinstance(sel, list):
             return a[sel]
+        if np.ndim(a) != 1:
+            return np.concatenate([a[b:e] for b, e in sel])
         n = sum(e - b for b, e in sel)
         stage = getattr(self, "_g_stage", None)
         if stage is None or stage.numel() != n:
@@ -1082,12 +1092,15 @@ class AdvectionDiffusion(ReactiveTransport):
         ctx.add_to_diagonal(self["pore.bc.outflow"])
         return f, nnz
 
-    def _run_slabs(self, solver, x0, x0_given):
-        # the slab path assembles the symmetric Laplacian only: outflow BCs and the
-        # (Nt,2) conductance would be dropped silently (round-1 advisor finding)
-        raise NotImplementedError(
-            "AdvectionDiffusion is not slab-parallel: under torchrun pass "
-            "B200PCG(distributed=False) to solve it on this rank's GPU")
+    # slab runs (torchrun): the rows of a slab are assembled from its throats with the
+    # two-way weights (b200_build_laplacian2_rows), every diagonal entry is kept explicit
+    # and the outflow values are added to the owned rows, as `_assemble` does on one GPU;
+    # the solve is the slab-parallel BiCGStab
+    def _slab_keep_diag(self):
+        return True
+
+    def _slab_after_assemble(self, ctx):
+        ctx.add_to_diagonal(self["pore.bc.outflow"])
 
     def rate(self, pores=[], throats=[], mode="group"):
         throats_i = self._parse_indices(throats)

@@ -448,6 +448,12 @@ extern "C" int b200_build_laplacian2(b200_ctx* ctx, const int64_t* conns, const 
   return build_laplacian_impl(ctx, conns, g2, 1, Np, Nt, 0, Np, nnz);
 }
 
+extern "C" int b200_build_laplacian2_rows(b200_ctx* ctx, const int64_t* conns, const double* g2,
+                                          int64_t Np, int64_t Nt, int64_t row_begin,
+                                          int64_t row_end, int64_t* nnz) {
+  return build_laplacian_impl(ctx, conns, g2, 1, Np, Nt, row_begin, row_end, nnz);
+}
+
 // diag[i] += add[i] where add is finite (AdvectionDiffusion outflow BC,
 // openpnm/algorithms/_advection_diffusion.py:86-105); the diagonal entry of the
 // system CSR is patched, so apply_bcs must have kept every diagonal entry

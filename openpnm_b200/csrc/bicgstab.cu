@@ -77,7 +77,10 @@ __global__ void __launch_bounds__(BI_T) k_bi_p(double* __restrict__ p,
 
 int b200_bicgstab(b200_ctx* ctx, const double* x0, double rtol, double atol, int64_t maxiter,
                   double* x, int64_t* iters, double* relres, int* info) {
-  if (ctx->nranks > 1) FAIL(B200_ERR_ARG, "BiCGStab: single GPU only");
+  // slab run (one rank per GPU): the operand of every product gets its halo windows from
+  // the neighbour ranks first, every dot product is all-reduced before it is consumed, and
+  // every decision is taken on all-reduced numbers (same control flow on all ranks)
+  const bool multi = ctx->nranks > 1;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   RET(b200_pcg_prepare(ctx, ctx->force_fmt));
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -110,16 +113,27 @@ int b200_bicgstab(b200_ctx* ctx, const double* x0, double rtol, double atol, int
   const int g = grid_for(n, BI_T);
   CK(cudaMemsetAsync(flags, 0, FLAG_COUNT * sizeof(int), ctx->stream));
   CK(cudaMemsetAsync(sc, 0, SC_COUNT * sizeof(double), ctx->stream));
+  // x_owned - pad = base of the padded vector whose halo windows are exchanged
+  auto halo = [&](double* owned) { return b200_halo_exchange(ctx, owned - pad); };
+  auto resid = [&]() -> int {                 // r = p = b~ - A~ x, rho = r.r, true residual norm
+    RET(halo(xt));
+    RET(b200_spmv_dots(ctx, xt, bt, v, sc + SC_AUX0));
+    RET(b200_launch_resid(ctx, bt, v, d, r, p, sc + B_RHO, sc + B_TRUE));
+    RET(b200_allreduce_sum(ctx, sc + B_RHO, 1));
+    RET(b200_allreduce_sum(ctx, sc + B_TRUE, 1));
+    return B200_OK;
+  };
   RET(b200_launch_init(ctx, x0, xt, bt, sc + SC_BNORM));
-  RET(b200_spmv_dots(ctx, xt, bt, v, sc + SC_AUX0));
-  RET(b200_launch_resid(ctx, bt, v, d, r, p, sc + B_RHO, sc + B_TRUE));   // rho = r.r (rhat = r)
+  RET(b200_allreduce_sum(ctx, sc + SC_BNORM, 1));
+  RET(resid());                                                            // rhat = r
   CK(cudaMemcpyAsync(rhat, r, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->scal_h, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost,
                      ctx->stream));
   CK(cudaMemcpyAsync(ctx->flags_h, flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost,
                      ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  if (ctx->flags_h[FLAG_NONFINITE] || !isfinite(ctx->scal_h[SC_BNORM]))
+  if ((!multi && ctx->flags_h[FLAG_NONFINITE]) || !isfinite(ctx->scal_h[SC_BNORM]) ||
+      !isfinite(ctx->scal_h[B_TRUE]))
     FAIL(B200_ERR_NONFINITE, "b or x0 contains inf/nan values");
   const double bnorm2 = ctx->scal_h[SC_BNORM];
   double tol2 = rtol * rtol * bnorm2;
@@ -137,10 +151,16 @@ int b200_bicgstab(b200_ctx* ctx, const double* x0, double rtol, double atol, int
   }
   bool done = !(true2 > tol2);
   while (!done && it < maxiter) {
+    RET(halo(p));
     RET(b200_spmv_dots(ctx, p, rhat, v, sc + B_G1));
+    RET(b200_allreduce_sum(ctx, sc + B_G1, 3));
     LAUNCH(ctx, k_bi_s, g, BI_T, 0, r, v, s, n, sc);
+    RET(halo(s));
     RET(b200_spmv_dots(ctx, s, rhat, t, sc + B_G2));
+    RET(b200_allreduce_sum(ctx, sc + B_G2, 3));
     LAUNCH(ctx, k_bi_x, g, BI_T, 0, xt, r, p, s, t, rhat, d, n, sc, part, ticket, sc);
+    RET(b200_allreduce_sum(ctx, sc + B_RHON, 1));
+    RET(b200_allreduce_sum(ctx, sc + B_RR, 2));
     LAUNCH(ctx, k_bi_p, g, BI_T, 0, p, r, v, n, sc);
     CK(cudaMemcpyAsync(ctx->scal_h, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost,
                        ctx->stream));
@@ -156,8 +176,7 @@ int b200_bicgstab(b200_ctx* ctx, const double* x0, double rtol, double atol, int
               true2, tol2, rho_new);
     if (!isfinite(true2) || !isfinite(rho_new)) { inf = -1; break; }
     if (true2 <= tol2) {
-      RET(b200_spmv_dots(ctx, xt, bt, v, sc + SC_AUX0));
-      RET(b200_launch_resid(ctx, bt, v, d, r, p, sc + B_RHO, sc + B_TRUE));
+      RET(resid());
       CK(cudaMemcpyAsync(rhat, r, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice,
                          ctx->stream));
       CK(cudaMemcpyAsync(ctx->scal_h, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost,
@@ -172,8 +191,7 @@ int b200_bicgstab(b200_ctx* ctx, const double* x0, double rtol, double atol, int
       // breakdown: restart from the current residual with a fresh shadow vector
       if (restarts >= 8) { inf = -1; break; }
       ++restarts;
-      RET(b200_spmv_dots(ctx, xt, bt, v, sc + SC_AUX0));
-      RET(b200_launch_resid(ctx, bt, v, d, r, p, sc + B_RHO, sc + B_TRUE));
+      RET(resid());
       CK(cudaMemcpyAsync(rhat, r, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice,
                          ctx->stream));
     }

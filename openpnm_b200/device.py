@@ -121,20 +121,22 @@ class Context:
         self.row_begin = int(row_begin)
         return nnz.value
 
-    def build_laplacian2(self, conns, g2, Np):
-        """(Nt,2) weights -> non-symmetric Laplacian (AdvectionDiffusion)."""
+    def build_laplacian2(self, conns, g2, Np, row_begin=0, row_end=None):
+        """(Nt,2) weights -> non-symmetric Laplacian (AdvectionDiffusion); rows
+        [row_begin, row_end) from the throats touching them in a slab run."""
         torch = _torch()
         conns = self.to_device(conns, torch.int64)
         g2 = self.to_device(np.ascontiguousarray(g2, dtype=np.float64), torch.float64)
         Nt = int(g2.numel() // 2)
         if conns.numel() != 2 * Nt:
             raise ValueError("conns must be (Nt, 2) and g2 (Nt, 2)")
+        row_end = int(Np) if row_end is None else int(row_end)
         nnz = C.c_int64()
-        self._ck(self.lib.b200_build_laplacian2(self._h, self._p(conns), self._p(g2), int(Np), Nt,
-                                                C.byref(nnz)))
+        self._ck(self.lib.b200_build_laplacian2_rows(self._h, self._p(conns), self._p(g2), int(Np),
+                                                     Nt, int(row_begin), row_end, C.byref(nnz)))
         self._keep["conns"], self._keep["g"] = conns, g2
-        self.n = int(Np)
-        self.row_begin = 0
+        self.n = row_end - int(row_begin)
+        self.row_begin = int(row_begin)
         return nnz.value
 
     def add_to_diagonal(self, add):

@@ -321,7 +321,11 @@ class SlabSolver:
         if reuse_laplacian and getattr(self, "_nnz_pure", None) is not None:
             f, nnz_sys = ctx.apply_bcs(bc_value, bc_rate, keep_zero_diag=keep_zero_diag)
             return f, self._nnz_pure, nnz_sys
-        nnz = ctx.build_laplacian(conns_local, g_local, self.Np, self.row_begin, self.row_end)
+        two_way = (g_local.dim() if hasattr(g_local, "dim") else np.ndim(g_local)) == 2
+        if two_way:      # (Nt,2) conductance of AdvectionDiffusion: non-symmetric rows
+            nnz = ctx.build_laplacian2(conns_local, g_local, self.Np, self.row_begin, self.row_end)
+        else:
+            nnz = ctx.build_laplacian(conns_local, g_local, self.Np, self.row_begin, self.row_end)
         self._nnz_pure = nnz
         if self.world > 1:
             s, c = ctx.pure_diag_sum()

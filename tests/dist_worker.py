@@ -202,6 +202,40 @@ def main():
     if rank == 0:
         print(f"dist ok delaunay Np={pn3.Np} Nt={pn3.Nt} band={bdist.bandwidth(pn3.conns)} "
               f"world={world} iters={its} fmt={fd._ctx.pcg_format()}", flush=True)
+    # ---- AdvectionDiffusion, slab-parallel: (Nt,2) upwind conductance from a pressure field,
+    # outflow BC, non-symmetric rows per slab, BiCGStab with halo exchange + all-reduced dots
+    pna = b2.Cubic((14, 9, 8), spacing=1e-4, coords=False)
+    rng = np.random.default_rng(0)
+    gh = 10.0 ** rng.uniform(-15, -14, pna.Nt)
+    gd = 10.0 ** rng.uniform(-15.5, -14.5, pna.Nt)
+    pha = b2.Phase(pna)
+    pha["throat.hydraulic_conductance"] = gh
+    sfa = b2.StokesFlow(network=pna, phase=pha)
+    sfa.set_value_BC(pores=pna.pores("right"), values=1.0)
+    sfa.set_value_BC(pores=pna.pores("left"), values=0.0)
+    sfa.run(solver=b2.B200PCG(tol=1e-13))
+    P = sfa.x
+    pha["pore.pressure"] = P
+    ca = pna.conns
+    Q = -gh * (P[ca[:, 1]] - P[ca[:, 0]])
+    g2 = np.column_stack((np.maximum(-Q, 0) + gd, np.maximum(Q, 0) + gd))
+    dict.__setitem__(pha, "throat.ad_dif_conductance", g2)
+    ad = b2.AdvectionDiffusion(network=pna, phase=pha)
+    ad.set_value_BC(pores=pna.pores("right"), values=2.0)
+    ad.set_outflow_BC(pores=pna.pores("left"))
+    taken = np.union1d(pna.pores("right"), pna.pores("left"))
+    ad.set_value_BC(pores=np.setdiff1d(pna.pores("top"), taken)[::3], values=0.3)
+    ad.run(solver=b2.B200PCG(tol=1e-13))
+    refa = oracle.picard_run(ca, g2, pna.Np, bc_value=ad["pore.bc.value"],
+                             bc_outflow=ad["pore.bc.outflow"])
+    erra = np.max(np.abs(ad.x - refa["x"])) / np.max(np.abs(refa["x"]))
+    assert ad.soln.is_converged and erra <= 1e-8, erra
+    Qt = g2[:, 0] * refa["x"][ca[:, 1]] - g2[:, 1] * refa["x"][ca[:, 0]]
+    np.testing.assert_allclose(ad.rate(throats=[0, 7, 50], mode="single"),
+                               np.abs(Qt[[0, 7, 50]]), rtol=1e-6, atol=1e-30)
+    if rank == 0:
+        print(f"dist ok advection-diffusion world={world} err={erra:.2e} "
+              f"iters={ad.soln.cg_iters} fmt={ad._ctx.pcg_format()}", flush=True)
     # ---- transient run, slab-parallel (RK45 on the device: halo exchange per right-hand
     # side, all-reduced error norms): same accepted steps and states as scipy's RK45
     shape = (16, 10, 8)
