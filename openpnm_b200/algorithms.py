@@ -720,6 +720,14 @@ class Transport(dict):
         if stage is None or stage.numel() != n:
             stage = torch.empty(n, dtype=torch.float64, pin_memory=True)
             self._x_stage = stage
+        # x_dev may have been produced on another stream (a slab run gathers it with
+        # torch.distributed on torch's current stream): order this context's stream after
+        # it, or the copy below could read the gathered tensor before it is complete --
+        # recycled allocator memory, e.g. an old NaN-filled BC buffer, instead of x
+        cur = torch.cuda.current_stream(x_dev.device)
+        if cur != ctx.stream:
+            ctx.stream.wait_stream(cur)
+            x_dev.record_stream(ctx.stream)
         with torch.cuda.stream(ctx.stream):
             stage.copy_(x_dev, non_blocking=True)
         ctx.synchronize()
@@ -1250,8 +1258,7 @@ def _run_transient_slabs(self, integrator, x0, V, tspan, saveat):
     self.soln.nsteps, self.soln.nfev = int(nsteps), int(nfev)
     if nout:
         dict.__setitem__(self, q, Yh[:, -1].copy())
-        with torch.cuda.stream(ctx.stream):
-            self._x_dev = Yfull[:, -1].contiguous()
+        self._x_dev = Yfull[:, -1].contiguous()     # on the stream that gathered Yfull
     self.stats = ctx.stats()
     self._post_run(self[q])
 

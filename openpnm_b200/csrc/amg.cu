@@ -502,6 +502,14 @@ __global__ void __launch_bounds__(AMG_T) k_amg_shift_ids(int64_t n, const int* _
   }
 }
 
+__global__ void k_amg_count_nonfinite(int64_t n, const double* __restrict__ a, int* cnt) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    if (!isfinite(a[i])) ++c;
+  if (c) atomicAdd(cnt, c);
+}
+
 // ============================================================== cycle kernels
 // Coarse-level product y = A x with the values held in fp32 (the coarse operators
 // only precondition: 8 instead of 12 bytes per entry); x, y and the sums stay fp64.
@@ -1186,6 +1194,20 @@ static int amg_setup(b200_ctx* ctx) {
   A->epoch = ctx->sys_epoch;
   A->lin_epoch = ctx->lin_epoch;
   if (ctx->debug) {
+    // how many non-finite numbers each level's matrix and inverse diagonal hold
+    for (size_t k = 1; k < A->nlev; ++k) {
+      int* cnt = ctx->w_flags.as<int>() + FLAG_COUNT - 2;
+      cudaMemsetAsync(cnt, 0, sizeof(int), ctx->stream);
+      k_amg_count_nonfinite<<<grid_for(A->lv[k].nnz, AMG_T), AMG_T, 0, ctx->stream>>>(
+          A->lv[k].nnz, A->lv[k].av, cnt);
+      k_amg_count_nonfinite<<<grid_for(A->lv[k].n, AMG_T), AMG_T, 0, ctx->stream>>>(
+          A->lv[k].n, A->lv[k].dv, cnt);
+      int h = 0;
+      cudaMemcpyAsync(&h, cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      fprintf(stderr, "[b200 amg r%d] level %d: %d non-finite values, halo %d/%d send %d/%d\n",
+              ctx->rank, (int)k, h, A->lv[k].wlo, A->lv[k].whi, A->lv[k].slo, A->lv[k].shi);
+    }
     fprintf(stderr, "[b200 amg r%d] levels:", ctx->rank);
     for (size_t k = 0; k < A->nlev; ++k)
       fprintf(stderr, " n=%lld/%lld nnz=%lld %s lmax=%.3f |", (long long)A->lv[k].n,
@@ -1468,8 +1490,8 @@ int b200_amg_pcg(b200_ctx* ctx, const double* x0, double rtol, double atol, int6
     true2 = ctx->scal_h[F_TRUE];
     const double dq = ctx->scal_h[F_DQ];
     if (ctx->debug)
-      fprintf(stderr, "[b200 amg] it=%lld true2=%.3e tol2=%.3e d.q=%.3e d.r=%.3e\n",
-              (long long)it, true2, tol2, dq, ctx->scal_h[F_DR]);
+      fprintf(stderr, "[b200 amg r%d] it=%lld true2=%.3e tol2=%.3e d.q=%.3e d.r=%.3e z.q=%.3e\n",
+              ctx->rank, (long long)it, true2, tol2, dq, ctx->scal_h[F_DR], ctx->scal_h[F_ZQ]);
     if (!isfinite(true2) || !isfinite(dq)) { inf = -1; break; }
     if (!(dq > 0.0)) { inf = -1; break; }
     if (true2 <= tol2) {
