@@ -567,9 +567,12 @@ def gpu_arm(args):
         return allmax((time.perf_counter() - t0) / reps), float(np.mean(its_)), float(qq)
 
     t_e2e, it_e2e, qq = e2e_leg("jacobi")
-    h2d = conns_h.nbytes + g_h.nbytes + 2 * bcv_h.nbytes    # per rank: its throats + the BC arrays
-    if world > 1:
-        h2d = int(allsum([h2d])[0])
+    if world == 1:
+        h2d = conns_h.nbytes + g_h.nbytes + 2 * bcv_h.nbytes
+    else:     # per rank: its slab's throats + conductances, and the window of the two BC arrays
+        # it reads (its rows + one halo plane on either side), summed over the ranks
+        win = min(re + n * n, Np) - max(rb - n * n, 0)
+        h2d = int(allsum([conns_h.nbytes + g_h.nbytes + 2 * 8 * win])[0])
     e2e = {"value": Np * it_e2e / t_e2e, "unit": "DOF*iter/s",
            "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(world * (8 * Np + 8 * left.size)),
