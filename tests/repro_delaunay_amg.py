@@ -1,4 +1,7 @@
-"""Minimal repro: slab multigrid on the small x-sorted Delaunay case of tests/dist_worker.py."""
+"""TEST INFRASTRUCTURE (lives under tests/ because it uses the oracle's Delaunay helper).
+Minimal repro: slab multigrid on the small x-sorted Delaunay case of tests/dist_worker.py,
+in a fresh process with the library's debug trace on.
+    torchrun --nproc-per-node 4 tests/repro_delaunay_amg.py"""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
