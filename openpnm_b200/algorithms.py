@@ -649,7 +649,7 @@ class Transport(dict):
             bdist.slab_ranges(self.Np, world)
         rb, re = ranges[rank]
         nx, ny, nz = (int(v) for v in shape) if lattice else (0, 0, 0)
-        analytic = type(net) is Cubic and lattice and \
+        analytic = type(net) is Cubic and lattice and getattr(net, "connectivity", 6) == 6 and \
             net.Nt == (nx - 1) * ny * nz + nx * (ny - 1) * nz + nx * ny * (nz - 1) and \
             not getattr(net, "_conns_touched", False)
         if analytic:

@@ -129,8 +129,25 @@ class Cubic(Network):
     labels left/right (x), front/back (y), bottom/top (z) and the xmin/xmax...
     aliases (_skgraph/generators/tools/_funcs.py:216-250)."""
 
-    def __init__(self, shape, spacing=1.0, coords=True, lazy=False):
-        """lazy=True keeps only the shape: 'throat.conns' (and 'throat.all') are generated
+    # neighbour offsets (dx, dy, dz) in the order the reference emits their throats
+    # (_cubic.py:40-67): faces, then the four body diagonals, then the face diagonals
+    _FACE_DIRS = ((0, 0, 1), (0, 1, 0), (1, 0, 0))
+    _CORNER_DIRS = ((1, 1, 1), (1, 1, -1), (1, -1, 1), (-1, 1, 1))
+    _EDGE_DIRS = ((0, 1, 1), (0, 1, -1), (1, 0, 1), (-1, 0, 1), (-1, -1, 0), (-1, 1, 0))
+
+    def _dirs(self):
+        try:
+            return {6: self._FACE_DIRS, 14: self._FACE_DIRS + self._CORNER_DIRS,
+                    18: self._FACE_DIRS + self._EDGE_DIRS,
+                    20: self._EDGE_DIRS + self._CORNER_DIRS,
+                    26: self._FACE_DIRS + self._CORNER_DIRS + self._EDGE_DIRS}[self.connectivity]
+        except KeyError:
+            raise Exception("Invalid connectivity. Must be 6, 14, 18, 20 or 26.") from None
+
+    def __init__(self, shape, spacing=1.0, coords=True, lazy=False, connectivity=6):
+        """connectivity: 6 (faces), 14 (+ body diagonals), 18 (+ face diagonals), 20
+        (diagonals only) or 26, as `op.network.Cubic`.
+        lazy=True keeps only the shape: 'throat.conns' (and 'throat.all') are generated
         when first read.  A slab-parallel run never reads them -- every rank derives the
         throats of its own planes from index arithmetic (openpnm_b200.dist) -- so a 400^3
         lattice costs no rank the 3 GB of the full list."""
@@ -140,11 +157,14 @@ class Cubic(Network):
         nx, ny, nz = (int(s) for s in shape)
         n = nx * ny * nz
         self.shape = (nx, ny, nz)
+        self.connectivity = int(connectivity)
         self.spacing = np.ones(3) * np.asarray(spacing, dtype=float)
+        dirs = self._dirs()
         if lazy:
             _Store.__init__(self)
             self._Np = n
-            self._Nt = (nx - 1) * ny * nz + nx * (ny - 1) * nz + nx * ny * (nz - 1)
+            self._Nt = sum(max(nx - abs(dx), 0) * max(ny - abs(dy), 0) * max(nz - abs(dz), 0)
+                           for dx, dy, dz in dirs)
             dict.__setitem__(self, "pore.all", np.ones(n, dtype=bool))
         else:
             super().__init__(coords=None, conns=self._lattice_conns(), Np=n)
@@ -155,6 +175,21 @@ class Cubic(Network):
 
     def _lattice_conns(self):
         nx, ny, nz = self.shape
+        if self.connectivity != 6:
+            # per offset: the pores whose neighbour at that offset exists, in index order,
+            # paired with that neighbour; each pair stored smaller index first
+            # (_cubic.py:69-77)
+            ax, ay, az = (np.arange(m, dtype=np.int64) for m in (nx, ny, nz))
+            parts = []
+            for dx, dy, dz in self._dirs():
+                xs, ys, zs = (a[(a + d >= 0) & (a + d < m)]
+                              for a, d, m in ((ax, dx, nx), (ay, dy, ny), (az, dz, nz)))
+                tails = ((xs[:, None, None] * ny + ys[None, :, None]) * nz
+                         + zs[None, None, :]).ravel()
+                heads = tails + (dx * ny + dy) * nz + dz
+                parts.append(np.stack((np.minimum(tails, heads), np.maximum(tails, heads)),
+                                      axis=1))
+            return np.concatenate(parts) if parts else np.zeros((0, 2), dtype=np.int64)
         idx = np.arange(nx * ny * nz, dtype=np.int64).reshape(nx, ny, nz)
         tails = np.concatenate((idx[:, :, :-1].ravel(), idx[:, :-1, :].ravel(),
                                 idx[:-1, :, :].ravel()))

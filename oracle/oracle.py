@@ -11,7 +11,11 @@ every function below against it, and commits the resulting vectors under
 `tests/golden/`; `tests/test_oracle_golden.py` re-checks the oracle against
 those vectors and against the known-answer constants of the reference's own
 tests (SolversTest, SubclassedTransportTest, GenericTransportTest,
-ReactiveTransportTest, Flow_in_straight_conduit).
+ReactiveTransportTest, Flow_in_straight_conduit).  Round 2 added the reference's
+check_network_health / cluster_size / topotools.trim (g15), Cubic connectivity
+6/14/18/26 with its SuperLU solves (g16) and ReactiveTransport with a conductance
+that follows the quantity through misc.polynomial -> misc.from_neighbor_pores ->
+generic_diffusive / generic_hydraulic (g17: same Picard count, x to 1e-10).
 
 Third-party arithmetic the reference delegates to (not vendored, not pinned by
 the reference: setup.py:46-64): scipy (this image: 1.18.1) --
@@ -31,7 +35,8 @@ __all__ = [
     "cubic_network", "adjacency_coo", "laplacian_coo", "build_A", "apply_bcs",
     "apply_sources", "to_csr", "source_term", "picard_run", "rate",
     "jacobi_pcg", "spsolve", "transport_run", "delaunay_network", "transient_run",
-    "apply_outflow", "outflow_values",
+    "apply_outflow", "outflow_values", "polynomial", "from_neighbor_pores",
+    "conduit_conductance", "network_health", "trim",
 ]
 
 
@@ -330,10 +335,14 @@ def picard_run(conns, g, Np, bc_value=None, bc_rate=None, sources=(), x0=None,
     """
     if solver is None:
         solver = lambda A, b, x0: spsolve(A, b)  # noqa: E731
-    pure = build_A(conns, g, Np)
+    pure = None if callable(g) else build_A(conns, g, Np)
 
     def update(x):
-        A, b, _ = apply_bcs(pure, Np, bc_value, bc_rate)
+        # a conductance that is itself an iterative property (g callable: g(x)) switches
+        # the cache off and the Laplacian is rebuilt from the regenerated values at every
+        # update (_transport.py:106-114 after _update_iterative_props, _algorithm.py:69-91)
+        A0 = build_A(conns, g(x), Np) if callable(g) else pure
+        A, b, _ = apply_bcs(A0, Np, bc_value, bc_rate)
         if bc_outflow is not None:
             A = apply_outflow(A, Np, bc_outflow)
         lin = []
@@ -433,6 +442,48 @@ def rate(conns, g, x, pores=None, throats=None, mode="group"):
     if mode == "group":
         R = np.sum(R)
     return np.array(R, ndmin=1)
+
+
+# ------------------------------------------------- conductance models
+def polynomial(a, x):
+    """models.misc.polynomial (openpnm/models/misc/_simple_equations.py:113-117):
+    sum of a[i] * x**i, accumulated in that order."""
+    x = np.asarray(x).astype(float)
+    value = 0.0
+    for i in range(len(a)):
+        value = value + a[i] * (x ** i)
+    return value
+
+
+def from_neighbor_pores(conns, pore_values, mode="min"):
+    """models.misc.from_neighbor_pores on all throats
+    (openpnm/models/misc/_neighbor_lookups.py:121-138), nan-free input."""
+    v = np.asarray(pore_values)[np.asarray(conns)]
+    return {"min": np.amin, "max": np.amax, "mean": np.mean, "sum": np.sum}[mode](v, axis=1)
+
+
+def conduit_conductance(kind, conns, pore_prop, throat_prop, size_factors):
+    """Series conductance of pore 1 | throat | pore 2.
+    kind 'hydraulic': generic_hydraulic (models/physics/hydraulic_conductance/_funcs.py:37-53),
+    g_i = F_i / mu_i, a 1-D size factor array is the throat's with F1 = F2 = inf;
+    kind 'poisson': _poisson_conductance (models/physics/_utils.py:46-61) behind
+    generic_diffusive / _thermal / _electrical, g_i = D_i * F_i, a 1-D size factor array is
+    the whole conduit's: g = D_throat * F."""
+    conns = np.asarray(conns)
+    p1, p2 = np.asarray(pore_prop)[conns].T
+    pt = np.asarray(throat_prop)
+    SF = np.asarray(size_factors)
+    if kind == "hydraulic":
+        F1, Ft, F2 = SF.T if SF.ndim > 1 else (np.inf, SF, np.inf)
+        g1, gt, g2 = F1 / p1, Ft / pt, F2 / p2
+    elif kind == "poisson":
+        if SF.ndim != 2:
+            return pt * SF
+        F1, Ft, F2 = SF.T
+        g1, gt, g2 = p1 * F1, pt * Ft, p2 * F2
+    else:
+        raise ValueError(kind)
+    return 1 / (1 / g1 + 1 / gt + 1 / g2)
 
 
 # ---------------------------------------------------------------- health + trim

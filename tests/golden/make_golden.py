@@ -494,6 +494,170 @@ def g14_advection_diffusion():
     print("g14 ok", {k: float(v["x"].mean()) for k, v in out.items()})
 
 
+def g15_health_trim():
+    # check_network_health (openpnm/utils/_health.py:40-98) and topotools.trim
+    # (openpnm/topotools/_topotools.py:157-229) on a Delaunay network whose long throats
+    # were cut (isolated pores + small clusters), with two looped throats added
+    pts = np.random.default_rng(8).random((1500, 3))
+    pts = pts[np.argsort(pts[:, 0], kind="stable")]
+    conns = oracle.delaunay_network(pts)
+    L = np.linalg.norm(pts[conns[:, 0]] - pts[conns[:, 1]], axis=1)
+    conns = np.vstack((conns[L < 0.11], [[7, 7], [900, 900]]))
+    pn = op.network.Network(coords=pts, conns=conns)
+    h = op.utils.check_network_health(pn)
+    size = np.array(op.models.network.cluster_size(pn))
+    ref = oracle.network_health(conns, pts.shape[0])
+    assert np.flatnonzero(ref["isolated"]).tolist() == list(h["isolated_pores"])
+    assert ref["disconnected"].tolist() == list(h["disconnected_pores"])
+    assert ref["looped"].tolist() == list(h["looped_throats"])
+    assert np.array_equal(ref["cluster_size"], size)
+    assert len(h["isolated_pores"]) > 0 and ref["n_clusters"] > 3, "case does not bite"
+    out = dict(coords=pts, conns=conns, cluster_size=size,
+               isolated=np.array(h["isolated_pores"], dtype=np.int64),
+               disconnected=np.array(h["disconnected_pores"], dtype=np.int64),
+               looped=np.array(h["looped_throats"], dtype=np.int64))
+    # trim 1: the suggested fix (everything outside the largest cluster); trim 2: some
+    # throats of what is left; trim 3: pores and throats together
+    op.topotools.trim(network=pn, pores=h["disconnected_pores"])
+    new, Pk, Tk = oracle.trim(conns, pts.shape[0], ref["disconnected"])
+    assert np.array_equal(new, pn["throat.conns"]) and np.allclose(pts[Pk], pn["pore.coords"])
+    out.update(trim1_conns=np.array(pn["throat.conns"]), trim1_coords=np.array(pn["pore.coords"]))
+    Ts = np.arange(3, pn.Nt, 11)
+    c1, n1 = np.array(pn["throat.conns"]), pn.Np
+    op.topotools.trim(network=pn, throats=Ts)
+    new, Pk, Tk = oracle.trim(c1, n1, throats=Ts)
+    assert np.array_equal(new, pn["throat.conns"]) and Pk.size == pn.Np
+    out.update(trim2_throats=Ts, trim2_conns=np.array(pn["throat.conns"]))
+    Ps, Ts3 = np.arange(5, pn.Np, 13), np.arange(0, pn.Nt, 29)
+    c2, n2, xyz2 = np.array(pn["throat.conns"]), pn.Np, np.array(pn["pore.coords"])
+    op.topotools.trim(network=pn, pores=Ps, throats=Ts3)
+    new, Pk, Tk = oracle.trim(c2, n2, pores=Ps, throats=Ts3)
+    assert np.array_equal(new, pn["throat.conns"]) and np.allclose(xyz2[Pk], pn["pore.coords"])
+    out.update(trim3_pores=Ps, trim3_throats=Ts3, trim3_conns=np.array(pn["throat.conns"]),
+               trim3_coords=np.array(pn["pore.coords"]))
+    save("g15_health_trim_1500", **out)
+    META["g15_health_trim_1500"] = dict(
+        n_clusters=int(ref["n_clusters"]), n_isolated=len(h["isolated_pores"]),
+        n_disconnected=len(h["disconnected_pores"]), Np_after=[int(n1), int(n2), int(pn.Np)],
+        Nt_after=[int(c1.shape[0]), int(c2.shape[0]), int(pn.Nt)])
+    print("g15", META["g15_health_trim_1500"])
+
+
+def g16_cubic_connectivity():
+    # openpnm/_skgraph/generators/_cubic.py:40-67: throat numbering of the 6 / 14 / 18 / 26
+    # neighbour lattices, and a StokesFlow solve on each (rows have 7 / 9 / 13 distinct
+    # super-diagonals: the DIA-sym operator's widest cases)
+    shape = [5, 4, 6]
+    out, meta = {}, {}
+    for c in (6, 14, 18, 26):
+        pn = op.network.Cubic(shape=shape, spacing=1e-4, connectivity=c)
+        conns = np.array(pn["throat.conns"])
+        g = 10.0 ** np.random.default_rng(c).uniform(-15, -12, pn.Nt)
+        ph = op.phase.Phase(network=pn)
+        ph["throat.hydraulic_conductance"] = g
+        sf = op.algorithms.StokesFlow(network=pn, phase=ph)
+        sf.set_value_BC(pores=pn.pores("left"), values=2e5)
+        sf.set_value_BC(pores=pn.pores("right"), values=1e5)
+        sf.run(solver=op.solvers.ScipySpsolve())
+        bcv = np.array(sf["pore.bc.value"], dtype=float)
+        check_oracle_linear(f"g16_c{c}", pn, g, bcv, None, sf)
+        A = csr_of(sf)
+        offs = np.unique(A.indices - np.repeat(np.arange(pn.Np), np.diff(A.indptr)))
+        out.update({f"conns_{c}": conns, f"g_{c}": g, f"x_{c}": np.array(sf.x),
+                    f"bc_value_{c}": bcv,
+                    f"rate_left_{c}": sf.rate(pores=pn.pores("left")),
+                    f"rate_right_{c}": sf.rate(pores=pn.pores("right"))})
+        meta[str(c)] = dict(Nt=int(pn.Nt), super_diagonals=int((offs > 0).sum()))
+        op.Workspace().clear()
+    out["shape"] = np.array(shape)
+    out["left"] = np.array(op.network.Cubic(shape=shape).pores("left"))
+    out["right"] = np.array(op.network.Cubic(shape=shape).pores("right"))
+    save("g16_cubic_connectivity_5x4x6", **out)
+    META["g16_cubic_connectivity_5x4x6"] = meta
+    print("g16", meta)
+
+
+def _oracle_chain(kind, conns, poly, mode, sf, throat_fixed=None):
+    def g_of_x(x):
+        pv = oracle.polynomial(poly, x)
+        tv = throat_fixed if throat_fixed is not None else \
+            oracle.from_neighbor_pores(conns, pv, mode)
+        return oracle.conduit_conductance(kind, conns, pv, tv, sf)
+    return g_of_x
+
+
+def g17_variable_conductance():
+    # the conductance follows the quantity through
+    # misc.polynomial (openpnm/models/misc/_simple_equations.py:88-117) ->
+    # misc.from_neighbor_pores (_neighbor_lookups.py:82-138) -> generic_diffusive /
+    # generic_hydraulic (physics/_utils.py:46-61, hydraulic_conductance/_funcs.py:37-53);
+    # ReactiveTransport re-assembles every Picard iteration (_transport.py:107-108)
+    mods = op.models
+    cases = [
+        ("diffusive_mean_sf3", "poisson", [1e-9, 0.0, 5e-11], "mean", 3, False),
+        ("diffusive_min_sf1", "poisson", [2e-9, 1e-10], "min", 1, False),
+        ("hydraulic_max_sf3", "hydraulic", [1e-3, 2e-5, 1e-6], "max", 3, False),
+        ("hydraulic_fixed_throat_sf3", "hydraulic", [1e-3, 0.0, 3e-6], None, 3, True),
+        ("hydraulic_mean_sf1", "hydraulic", [1e-3, 4e-5], "mean", 1, False),
+    ]
+    meta = {}
+    for name, kind, poly, mode, sfc, fixed in cases:
+        rng = np.random.default_rng(4)
+        pn = op.network.Cubic(shape=[6, 5, 4])
+        conns = np.array(pn["throat.conns"])
+        sf = rng.uniform(0.5, 2.0, (pn.Nt, 3) if sfc == 3 else pn.Nt) * 1e-3
+        ph = op.phase.Phase(network=pn)
+        q = "pore.concentration" if kind == "poisson" else "pore.pressure"
+        ph[q] = 0.0
+        if kind == "poisson":
+            pkey, tkey, gkey, skey = ("pore.diffusivity", "throat.diffusivity",
+                                      "throat.diffusive_conductance",
+                                      "throat.diffusive_size_factors")
+            gmodel = mods.physics.diffusive_conductance.generic_diffusive
+            gargs = dict(pore_diffusivity=pkey, throat_diffusivity=tkey, size_factors=skey)
+        else:
+            pkey, tkey, gkey, skey = ("pore.viscosity", "throat.viscosity",
+                                      "throat.hydraulic_conductance",
+                                      "throat.hydraulic_size_factors")
+            gmodel = mods.physics.hydraulic_conductance.generic_hydraulic
+            gargs = dict(pore_viscosity=pkey, throat_viscosity=tkey, size_factors=skey)
+        pn[skey] = sf
+        ph.add_model(propname=pkey, model=mods.misc.polynomial, a=poly, prop=q)
+        tfix = None
+        if fixed:
+            tfix = rng.uniform(1.0, 2.0, pn.Nt) * poly[0]
+            ph[tkey] = tfix
+        else:
+            ph.add_model(propname=tkey, model=mods.misc.from_neighbor_pores, prop=pkey,
+                         mode=mode)
+        ph.add_model(propname=gkey, model=gmodel, **gargs)
+        ph.regenerate_models()
+        alg = op.algorithms.ReactiveTransport(network=pn, phase=ph)
+        alg.settings._update({"conductance": gkey, "quantity": q})
+        alg.set_value_BC(pores=pn.pores("front"), values=10.0)
+        alg.set_value_BC(pores=pn.pores("back"), values=0.0)
+        alg.run(solver=op.solvers.ScipySpsolve())
+        assert alg.soln.is_converged and alg.soln.num_iter > 2, name
+        bcv = np.array(alg["pore.bc.value"], dtype=float)
+        o = oracle.picard_run(conns, _oracle_chain(kind, conns, poly, mode, sf, tfix),
+                              pn.Np, bc_value=bcv)
+        assert o["num_iter"] == alg.soln.num_iter, (name, o["num_iter"], alg.soln.num_iter)
+        assert np.allclose(o["x"], alg.x, rtol=1e-10, atol=1e-13), name
+        gfin = np.array(ph[gkey], dtype=float)
+        assert np.allclose(_oracle_chain(kind, conns, poly, mode, sf, tfix)(alg.x), gfin,
+                           rtol=1e-13, atol=0), name
+        save("g17_variable_g_" + name, conns=conns, size_factors=sf, poly=np.array(poly),
+             throat_fixed=np.zeros(0) if tfix is None else tfix, bc_value=bcv,
+             x=np.array(alg.x), g_final=gfin, pore_prop_final=np.array(ph[pkey]),
+             rate_front=alg.rate(pores=pn.pores("front")),
+             rate_back=alg.rate(pores=pn.pores("back")))
+        meta[name] = dict(kind=kind, mode=mode, num_iter=int(alg.soln.num_iter),
+                          quantity=q, shape=[6, 5, 4])
+        op.Workspace().clear()
+    META["g17_variable_g"] = meta
+    print("g17", meta)
+
+
 def g8_big():
     # config 1 scale: Cubic 50^3, SuperLU (~3 min)
     n = 50
@@ -515,7 +679,8 @@ if __name__ == "__main__":
     if os.path.exists(meta_path):
         META.update(json.load(open(meta_path)))
     cases = [g1_solvers, g2_stokes, g3_reactive, g4_csr, g5_conduit, g6_profiles,
-             g7_hetero, g11_irregular, g13_transient, g14_advection_diffusion]
+             g7_hetero, g11_irregular, g13_transient, g14_advection_diffusion,
+             g15_health_trim, g16_cubic_connectivity, g17_variable_conductance]
     if args.big:
         cases = [g8_big]
     for fn in cases:

@@ -228,3 +228,32 @@ def test_host_copy_threads():
     assert b is not a and np.array_equal(a, b)
     c = _host_copy(a[:1000])
     assert np.array_equal(c, a[:1000])
+
+
+@pytest.mark.parametrize("c", [6, 14, 18, 26])
+def test_cubic_connectivity_matches_reference_numbering(c, golden):
+    """`Cubic(connectivity=...)`: the same throats, in the same order, as the reference's
+    generator (openpnm/_skgraph/generators/_cubic.py:40-67; fixture made by the real
+    reference, tests/golden/make_golden.py g16)"""
+    g = golden("g16_cubic_connectivity_5x4x6")
+    pn = b2.Cubic([int(v) for v in g["shape"]], spacing=1e-4, connectivity=c)
+    assert np.array_equal(pn["throat.conns"], g[f"conns_{c}"])
+    assert np.array_equal(pn.pores("left"), g["left"])
+    assert np.array_equal(pn.pores("right"), g["right"])
+
+
+def test_cubic_connectivity_lazy_and_invalid():
+    from openpnm_b200.network import Cubic
+    for shape in [(5, 4, 6), (5, 1, 4), (3, 3, 1), (1, 1, 7)]:
+        for c in (6, 14, 18, 20, 26):
+            eager, lazy = Cubic(shape, connectivity=c), Cubic(shape, connectivity=c, lazy=True)
+            assert lazy.Nt == eager.Nt == eager["throat.conns"].shape[0]
+            assert np.array_equal(lazy.conns, eager.conns)
+            assert (eager.conns[:, 0] < eager.conns[:, 1]).all()
+            # every pore pair at most once
+            assert np.unique(eager.conns, axis=0).shape[0] == eager.Nt
+    nx, ny, nz = 5, 4, 6
+    assert Cubic((nx, ny, nz), connectivity=26).Nt == \
+        Cubic((nx, ny, nz), connectivity=6).Nt + Cubic((nx, ny, nz), connectivity=20).Nt
+    with pytest.raises(Exception, match="Invalid connectivity"):
+        Cubic((3, 3, 3), connectivity=8)

@@ -167,3 +167,94 @@ def test_advection_diffusion_oracle(name, golden):
         np.testing.assert_allclose(ov[m], g["bc_outflow"][m], rtol=1e-12)
     if name == "g14_ad_4x3x1_powerlaw":
         np.testing.assert_allclose(g["x"][3:9], [0.89653] * 3 + [1.53924] * 3, rtol=1e-5)
+
+
+# ----------------------------------------------------------------- round-2 rows
+def test_network_health_and_trim(golden, golden_meta):
+    """oracle.network_health / oracle.trim against the reference's
+    check_network_health, cluster_size model and three successive topotools.trim calls."""
+    g = golden("g15_health_trim_1500")
+    m = golden_meta["g15_health_trim_1500"]
+    conns, Np = g["conns"], g["coords"].shape[0]
+    h = oracle.network_health(conns, Np)
+    assert h["n_clusters"] == m["n_clusters"]
+    assert np.array_equal(np.flatnonzero(h["isolated"]), g["isolated"])
+    assert np.array_equal(h["disconnected"], g["disconnected"])
+    assert np.array_equal(h["looped"], g["looped"])
+    assert np.array_equal(h["cluster_size"], g["cluster_size"])
+    assert g["isolated"].size == m["n_isolated"] > 0
+    c1, Pk, Tk = oracle.trim(conns, Np, pores=g["disconnected"])
+    assert np.array_equal(c1, g["trim1_conns"])
+    assert np.array_equal(g["coords"][Pk], g["trim1_coords"])
+    assert (Pk.size, Tk.size) == (m["Np_after"][0], m["Nt_after"][0])
+    assert oracle.network_health(c1, Pk.size)["disconnected"].size == 0
+    c2, Pk2, Tk2 = oracle.trim(c1, Pk.size, throats=g["trim2_throats"])
+    assert np.array_equal(c2, g["trim2_conns"]) and Pk2.size == m["Np_after"][1]
+    c3, Pk3, Tk3 = oracle.trim(c2, Pk2.size, pores=g["trim3_pores"], throats=g["trim3_throats"])
+    assert np.array_equal(c3, g["trim3_conns"])
+    assert np.array_equal(g["trim1_coords"][Pk3], g["trim3_coords"])
+    assert (Pk3.size, Tk3.size) == (m["Np_after"][2], m["Nt_after"][2])
+
+
+@pytest.mark.parametrize("c", [6, 14, 18, 26])
+def test_cubic_connectivity_solve(c, golden, golden_meta):
+    """Lattices with 14 / 18 / 26 neighbours (openpnm/_skgraph/generators/_cubic.py:40-67):
+    the reference's throat list, its SuperLU solution and rates; the operator has
+    7 / 9 / 13 super-diagonals, the widest cases of the DIA-sym format."""
+    g = golden("g16_cubic_connectivity_5x4x6")
+    conns, gv, bcv = g[f"conns_{c}"], g[f"g_{c}"], g[f"bc_value_{c}"]
+    Np = int(np.prod(g["shape"]))
+    out = oracle.transport_run(conns, gv, Np, bc_value=bcv)
+    np.testing.assert_allclose(out["x"], g[f"x_{c}"], rtol=1e-9, atol=0)
+    for side in ("left", "right"):
+        r = oracle.rate(conns, gv, out["x"], pores=g[side])
+        np.testing.assert_allclose(r, g[f"rate_{side}_{c}"], rtol=1e-8)
+    M = oracle.to_csr(oracle.apply_bcs(oracle.build_A(conns, gv, Np), Np, bcv, None)[0], Np)
+    offs = np.unique(M.indices - np.repeat(np.arange(Np), np.diff(M.indptr)))
+    assert int((offs > 0).sum()) == golden_meta["g16_cubic_connectivity_5x4x6"][str(c)][
+        "super_diagonals"] == {6: 3, 14: 7, 18: 9, 26: 13}[c]
+
+
+VARIABLE_G = ["diffusive_mean_sf3", "diffusive_min_sf1", "hydraulic_max_sf3",
+              "hydraulic_fixed_throat_sf3", "hydraulic_mean_sf1"]
+
+
+def variable_g_chain(g, meta):
+    """g(x) of a g17 fixture: polynomial -> neighbour interpolation (or a fixed throat
+    property) -> conduit conductance, from the oracle's restatements."""
+    conns, poly, sf = g["conns"], g["poly"], g["size_factors"]
+    fixed = g["throat_fixed"] if g["throat_fixed"].size else None
+
+    def g_of_x(x):
+        pv = oracle.polynomial(poly, x)
+        tv = fixed if fixed is not None else oracle.from_neighbor_pores(conns, pv, meta["mode"])
+        return oracle.conduit_conductance(meta["kind"], conns, pv, tv, sf)
+    return g_of_x
+
+
+@pytest.mark.parametrize("name", VARIABLE_G)
+def test_variable_conductance_picard(name, golden, golden_meta):
+    """a conductance that follows the quantity (the reference's
+    misc.polynomial -> misc.from_neighbor_pores -> generic_diffusive / generic_hydraulic,
+    run by its ReactiveTransport with SuperLU): same number of Picard iterations, same
+    x, same conductance left on the phase, same rates."""
+    g = golden("g17_variable_g_" + name)
+    meta = golden_meta["g17_variable_g"][name]
+    Np = int(np.prod(meta["shape"]))
+    chain = variable_g_chain(g, meta)
+    out = oracle.picard_run(g["conns"], chain, Np, bc_value=g["bc_value"])
+    assert out["is_converged"] and out["num_iter"] == meta["num_iter"] > 2
+    np.testing.assert_allclose(out["x"], g["x"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(oracle.polynomial(g["poly"], g["x"]), g["pore_prop_final"],
+                               rtol=1e-14)
+    gfin = chain(g["x"])
+    np.testing.assert_allclose(gfin, g["g_final"], rtol=1e-13, atol=0)
+    front = np.flatnonzero(g["bc_value"] == 10.0)
+    back = np.flatnonzero(g["bc_value"] == 0.0)
+    np.testing.assert_allclose(oracle.rate(g["conns"], gfin, g["x"], pores=front),
+                               g["rate_front"], rtol=1e-9)
+    np.testing.assert_allclose(oracle.rate(g["conns"], gfin, g["x"], pores=back),
+                               g["rate_back"], rtol=1e-9)
+    # the nonlinearity bites: the linear problem with g(0) has a different solution
+    lin = oracle.transport_run(g["conns"], chain(np.zeros(Np)), Np, bc_value=g["bc_value"])
+    assert np.max(np.abs(lin["x"] - g["x"])) > 1e-2
