@@ -257,3 +257,30 @@ def test_cubic_connectivity_lazy_and_invalid():
         Cubic((nx, ny, nz), connectivity=6).Nt + Cubic((nx, ny, nz), connectivity=20).Nt
     with pytest.raises(Exception, match="Invalid connectivity"):
         Cubic((3, 3, 3), connectivity=8)
+
+
+def test_slab_plan_analytic_lattice_equals_the_masked_plan():
+    """Transport._slab_plan: the index-arithmetic plan of a 6-neighbour lattice selects the
+    same throats as masking the full list; a lattice with diagonal neighbours (or one whose
+    conns were replaced) takes the masked plan and reports the true bandwidth"""
+    from openpnm_b200 import dist as bdist
+    from openpnm_b200.network import Cubic
+    shape = (9, 4, 5)
+    for world in (2, 3):
+        for rank in range(world):
+            pn = Cubic(shape, lazy=True)
+            alg = b2.Transport(network=pn, phase=b2.Phase(pn))
+            rb, re, band, sel, conns_loc = alg._slab_plan(world, rank)
+            assert "throat.conns" not in pn.keys()            # never materialised
+            full = Cubic(shape).conns
+            ids = np.flatnonzero(bdist.slab_throat_mask(full, rb, re))
+            ids_plan = np.concatenate([np.arange(a, b) for a, b in sel])
+            assert np.array_equal(ids_plan, ids) and np.array_equal(conns_loc, full[ids])
+            assert band == shape[1] * shape[2] == bdist.bandwidth(full)
+            # 26 neighbours: not the analytic form
+            pd = Cubic(shape, connectivity=26)
+            alg = b2.Transport(network=pd, phase=b2.Phase(pd))
+            rb2, re2, band2, sel2, loc2 = alg._slab_plan(world, rank)
+            assert (rb2, re2) == (rb, re) and not isinstance(sel2, list)
+            assert band2 == bdist.bandwidth(pd.conns) == shape[1] * shape[2] + shape[2] + 1
+            assert np.array_equal(loc2, pd.conns[bdist.slab_throat_mask(pd.conns, rb, re)])
