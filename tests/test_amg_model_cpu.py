@@ -112,3 +112,32 @@ def test_distributed_setup_needs_only_the_halo_of_the_aggregation_map():
         P = ref[0].P.tocsr()
         k = maps[0] >= 0
         assert np.array_equal(P.indices, maps[0][k]) and P.nnz == k.sum()
+
+
+def test_box_aggregation_keeps_every_level_a_lattice_operator():
+    """tests/models/amg_boxes.py (what DESIGN section 10 names as the next step for lattices):
+    2x2x2 boxes of the index lattice as aggregates -> every Galerkin operator is a 7-point
+    lattice operator (3 super-diagonals at (1, cz, cy*cz): the DIA-sym format of the fine
+    level serves all levels), still symmetric with non-positive off-diagonals, and the
+    outer iteration count is not worse than with pairwise matching on the benchmark's
+    conductance field"""
+    import amg_boxes
+    shape = (24, 20, 18)
+    A, b = problem(shape)
+    levels = amg_boxes.setup(A, shape, coarsest=400)
+    assert [L.shape for L in levels[:3]] == [(24, 20, 18), (12, 10, 9), (6, 5, 5)]
+    for L in levels:
+        cy, cz = L.shape[1], L.shape[2]
+        assert set(amg_boxes.super_diagonals(L.A)) <= {1, cz, cy * cz}
+        assert abs(L.A - L.A.T).max() <= 1e-12 * abs(L.A).max()
+        off = L.A - sp.diags(L.A.diagonal())
+        assert off.max() <= 0.0
+    # coarse couplings = the conductance crossing the box face (structured reduction)
+    L0, L1 = levels[0], levels[1]
+    agg, cs = amg_boxes.box_aggregates(L0.A, shape)
+    C = L0.A.tocoo()
+    m = (agg[C.row] == 0) & (agg[C.col] == 1)
+    assert np.isclose(L1.A[0, 1], C.data[m].sum(), rtol=1e-14)
+    its_box = solve(A, b, levels)
+    its_match = solve(A, b, amg_v2.setup(A, passes=3, passes0=4, coarsest=400))
+    assert its_box <= its_match + 2 and its_box <= 40, (its_box, its_match)
