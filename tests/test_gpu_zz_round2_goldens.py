@@ -78,7 +78,7 @@ def polynomial(target, a, prop):                  # models/misc/_simple_equation
 
 def from_neighbor_pores(target, prop, mode="min"):     # models/misc/_neighbor_lookups.py:121-138
     v = target[prop][target.network.conns]
-    return {"min": v.min(axis=1), "max": v.max(axis=1), "mean": v.mean(axis=1)}[mode]
+    return {"min": np.amin, "max": np.amax, "mean": np.mean, "sum": np.sum}[mode](v, axis=1)
 
 
 def generic_diffusive(target, pore_diffusivity="pore.diffusivity",

@@ -284,3 +284,61 @@ def test_slab_plan_analytic_lattice_equals_the_masked_plan():
             assert (rb2, re2) == (rb, re) and not isinstance(sel2, list)
             assert band2 == bdist.bandwidth(pd.conns) == shape[1] * shape[2] + shape[2] + 1
             assert np.array_equal(loc2, pd.conns[bdist.slab_throat_mask(pd.conns, rb, re)])
+
+
+def _variable_g_alg(poly=(1e-9, 0.0, 5e-11), mode="mean", sf_cols=3, gname="generic_diffusive",
+                    pname="polynomial", fixed_throat=False, extra=False):
+    """ReactiveTransport whose conductance follows the quantity through three phase models
+    (restated reference models, recognised by name)"""
+    import test_gpu_zz_round2_goldens as R
+    net = b2.Cubic([4, 3, 3])
+    rng = np.random.default_rng(0)
+    net["throat.diffusive_size_factors"] = rng.uniform(0.5, 2.0, (net.Nt, 3) if sf_cols == 3
+                                                       else net.Nt)
+    phase = b2.Phase(net)
+    phase["pore.concentration"] = 0.0
+
+    def other(target, a, prop):
+        return R.polynomial(target, a, prop)
+    pmodel = {"polynomial": R.polynomial, "other": other}[pname]
+    gmodel = {"generic_diffusive": R.generic_diffusive}[gname]
+    phase.add_model(propname="pore.diffusivity", model=pmodel, a=list(poly),
+                    prop="pore.concentration")
+    if fixed_throat:
+        phase["throat.diffusivity"] = np.full(net.Nt, 2e-9)
+    else:
+        phase.add_model(propname="throat.diffusivity", model=R.from_neighbor_pores,
+                        prop="pore.diffusivity", mode=mode)
+    phase.add_model(propname="throat.diffusive_conductance", model=gmodel,
+                    pore_diffusivity="pore.diffusivity", throat_diffusivity="throat.diffusivity",
+                    size_factors="throat.diffusive_size_factors")
+    if extra:      # one more property that follows the quantity through Python
+        phase.add_model(propname="pore.extra", model=other, a=[0.0, 1.0], prop="pore.concentration")
+    phase.regenerate_models()
+    alg = b2.ReactiveTransport(network=net, phase=phase)
+    alg.settings._update({"conductance": "throat.diffusive_conductance",
+                          "quantity": "pore.concentration"})
+    return net, phase, alg
+
+
+def test_device_conductance_plan_detection():
+    """Transport._device_conductance_plan: the polynomial -> neighbour interpolation ->
+    generic_* chain is handed to the device kernels; anything else keeps the host hook"""
+    net, phase, alg = _variable_g_alg()
+    plan = alg._device_conductance_plan(alg.iterative_props)
+    assert plan["kind"] == "poisson" and plan["interp"] == "mean" and plan["throat_prop"] is None
+    assert np.array_equal(plan["poly"], [1e-9, 0.0, 5e-11])
+    assert plan["size_factors"].shape == (net.Nt, 3) and plan["pore_prop"] == "pore.diffusivity"
+    for mode in ("min", "max"):
+        assert _variable_g_alg(mode=mode)[2]._device_conductance_plan(
+            ["pore.diffusivity", "throat.diffusivity", "throat.diffusive_conductance"]
+        )["interp"] == mode
+    net, phase, alg = _variable_g_alg(sf_cols=1)
+    assert alg._device_conductance_plan(alg.iterative_props)["size_factors"].shape == (net.Nt,)
+    net, phase, alg = _variable_g_alg(fixed_throat=True)
+    plan = alg._device_conductance_plan(alg.iterative_props)
+    assert plan["throat_prop"].shape == (net.Nt,) and np.all(plan["throat_prop"] == 2e-9)
+    # not the chain: host hook
+    for kw in (dict(mode="sum"), dict(pname="other"), dict(poly=[1.0] * 9), dict(extra=True)):
+        net, phase, alg = _variable_g_alg(**kw)
+        assert alg._device_conductance_plan(alg.iterative_props) is None, kw
