@@ -342,3 +342,47 @@ def test_device_conductance_plan_detection():
     for kw in (dict(mode="sum"), dict(pname="other"), dict(poly=[1.0] * 9), dict(extra=True)):
         net, phase, alg = _variable_g_alg(**kw)
         assert alg._device_conductance_plan(alg.iterative_props) is None, kw
+
+
+def test_solution_containers_behave_like_the_reference():
+    """openpnm/algorithms/_solution.py:15-84: SteadyStateSolution is a VIEW of its array
+    (the aliasing the Picard loop's first-iteration quirk rests on), TransientSolution
+    interpolates linearly in time, keeps `.t` through slicing, refuses times outside tspan"""
+    from openpnm_b200.algorithms import SteadyStateSolution, TransientSolution, Settings
+    x = np.arange(5.0)
+    s = SteadyStateSolution(x)
+    s[:] = 7.0
+    assert np.all(x == 7.0) and isinstance(s, np.ndarray)
+    t = np.array([0.0, 1.0, 3.0])
+    y = np.array([[0.0, 2.0, 6.0], [1.0, 1.0, 5.0]])          # (Np, len(t))
+    sol = TransientSolution(t, y)
+    assert np.array_equal(sol.t, t) and sol.shape == (2, 3)
+    np.testing.assert_allclose(sol(0.5), [1.0, 1.0])
+    np.testing.assert_allclose(sol.interpolate(2.0), [4.0, 3.0])
+    np.testing.assert_allclose(sol([1.0, 3.0]), y[:, 1:])
+    assert np.array_equal(sol[:, -1], [6.0, 5.0]) and np.array_equal(sol[0:1].t, t)
+    with pytest.raises(ValueError):
+        sol(3.5)
+    st = Settings(a=1)
+    st.b = 2
+    st._update({"c": 3})
+    assert (st.a, st["b"], st.c) == (1, 2, 3)
+    with pytest.raises(AttributeError):
+        st.missing
+
+
+def test_clearing_bcs():
+    # openpnm/algorithms/_algorithm.py:93-103, BCTest.py
+    pn = b2.Cubic([3, 3, 3])
+    alg = b2.Transport(network=pn, phase=b2.Phase(pn))
+    alg.set_value_BC(pores=pn.pores("left"), values=1.0)
+    alg.set_rate_BC(pores=pn.pores("right"), rates=2.0)
+    alg.clear_value_BCs()
+    assert np.isnan(alg["pore.bc.value"]).all() and np.isfinite(alg["pore.bc.rate"]).sum() == 9
+    alg.set_value_BC(pores=pn.pores("left"), values=1.0)
+    alg.clear_rate_BCs()
+    assert np.isnan(alg["pore.bc.rate"]).all() and np.isfinite(alg["pore.bc.value"]).sum() == 9
+    alg.set_rate_BC(pores=pn.pores("right"), rates=2.0)
+    alg.clear_BCs()
+    assert np.isnan(alg["pore.bc.rate"]).all() and np.isnan(alg["pore.bc.value"]).all()
+    assert np.array_equal(alg.Ps, np.arange(27)) and alg.Ts.size == pn.Nt
