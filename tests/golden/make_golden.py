@@ -670,6 +670,48 @@ def g8_big():
     del alg
 
 
+def g18_config1():
+    # BASELINE config 1 / SURVEY 8d, literally: Cubic 50^3, spheres_and_cylinders geometry with
+    # np.random.seed(0), viscosity 1e-3, physics.basic -> generic_hydraulic, left 2e5 / right 1e5,
+    # ScipySpsolve (SuperLU, ~3 min).  The conductances come out of the reference's geometry
+    # models, so they are stored (float64) with the solution.
+    n = 50
+    np.random.seed(0)
+    pn = op.network.Cubic(shape=[n, n, n], spacing=1e-4)
+    pn.add_model_collection(op.models.collections.geometry.spheres_and_cylinders)
+    pn.regenerate_models()
+    ph = op.phase.Phase(network=pn)
+    ph["pore.viscosity"] = 1e-3
+    ph.add_model_collection(op.models.collections.physics.basic)
+    ph.regenerate_models()
+    g = np.array(ph["throat.hydraulic_conductance"], dtype=float)
+    sf = op.algorithms.StokesFlow(network=pn, phase=ph)
+    sf.set_value_BC(pores=pn.pores("left"), values=2e5)
+    sf.set_value_BC(pores=pn.pores("right"), values=1e5)
+    t0 = time.time()
+    sf.run(solver=op.solvers.ScipySpsolve())
+    dt = time.time() - t0
+    x = np.array(sf.x)
+    bcv = np.array(sf["pore.bc.value"], dtype=float)
+    A = csr_of(sf)
+    # oracle: same system bit for bit in structure, same b; the reference's x solves it
+    pure = oracle.build_A(pn["throat.conns"], g, pn.Np)
+    Ao, b, f = oracle.apply_bcs(pure, pn.Np, bcv, None)
+    Ao = oracle.to_csr(Ao, pn.Np)
+    assert np.array_equal(Ao.indptr, A.indptr) and np.array_equal(Ao.indices, A.indices)
+    assert np.allclose(Ao.data, A.data, rtol=1e-13, atol=0) and np.allclose(b, sf.b, rtol=1e-12)
+    relres = np.linalg.norm(Ao @ x - b) / np.linalg.norm(b)
+    rl, rr = sf.rate(pores=pn.pores("left"))[0], sf.rate(pores=pn.pores("right"))[0]
+    assert np.isclose(oracle.rate(pn["throat.conns"], g, x, pores=pn.pores("left"))[0], rl,
+                      rtol=1e-10)
+    save("g18_config1_cubic50_spheres_and_cylinders", g=g, x=x)
+    META["g18_config1_cubic50_spheres_and_cylinders"] = dict(
+        Np=int(pn.Np), Nt=int(pn.Nt), nnz=int(A.nnz), f=float(f), g_min=float(g.min()),
+        g_max=float(g.max()), g_mean=float(g.mean()), rate_left=float(rl), rate_right=float(rr),
+        relres_of_reference_x=float(relres), ref_seconds=round(dt, 1))
+    print("g18", META["g18_config1_cubic50_spheres_and_cylinders"])
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--big", action="store_true")
@@ -682,7 +724,7 @@ if __name__ == "__main__":
              g7_hetero, g11_irregular, g13_transient, g14_advection_diffusion,
              g15_health_trim, g16_cubic_connectivity, g17_variable_conductance]
     if args.big:
-        cases = [g8_big]
+        cases = [g8_big, g18_config1]
     for fn in cases:
         if args.only and args.only not in fn.__name__:
             continue

@@ -157,3 +157,23 @@ def test_variable_conductance_against_the_reference_fixture(b2, golden, golden_m
     nt.assert_allclose(phase[pkey], g["pore_prop_final"], rtol=1e-8)
     nt.assert_allclose(alg.rate(pores=net.pores("front")), g["rate_front"], rtol=1e-7)
     nt.assert_allclose(alg.rate(pores=net.pores("back")), g["rate_back"], rtol=1e-7)
+
+
+@pytest.mark.parametrize("precond", ["jacobi", "amg"])
+def test_config1_as_stated_against_the_reference_fixture(b2, golden, golden_meta, precond):
+    """BASELINE config 1, literally (spheres_and_cylinders geometry, physics.basic, SuperLU
+    by the reference): x within 1e-8 relative, both rates, the system's nnz."""
+    name = "g18_config1_cubic50_spheres_and_cylinders"
+    g, m = golden(name), golden_meta[name]
+    pn = b2.Cubic([50, 50, 50], spacing=1e-4, coords=False)
+    ph = b2.Phase(pn)
+    ph["throat.hydraulic_conductance"] = g["g"]
+    sf = b2.StokesFlow(network=pn, phase=ph)
+    sf.set_value_BC(pores=pn.pores("left"), values=2e5)
+    sf.set_value_BC(pores=pn.pores("right"), values=1e5)
+    sf.run(solver=b2.B200PCG(tol=1e-13, precond=precond))
+    assert sf.soln.is_converged and sf.A.nnz == m["nnz"]
+    assert np.max(np.abs(sf.x - g["x"]) / np.abs(g["x"])) < 1e-8
+    for side in ("left", "right"):
+        r = sf.rate(pores=pn.pores(side))[0]
+        assert abs(r - m["rate_" + side]) <= 1e-8 * abs(m["rate_" + side])

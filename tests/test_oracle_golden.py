@@ -258,3 +258,30 @@ def test_variable_conductance_picard(name, golden, golden_meta):
     # the nonlinearity bites: the linear problem with g(0) has a different solution
     lin = oracle.transport_run(g["conns"], chain(np.zeros(Np)), Np, bc_value=g["bc_value"])
     assert np.max(np.abs(lin["x"] - g["x"])) > 1e-2
+
+
+def test_config1_as_stated(golden, golden_meta):
+    """BASELINE config 1 / SURVEY 8d, literally: Cubic 50^3 with the reference's
+    spheres_and_cylinders geometry (np.random.seed(0)) and physics.basic conductances,
+    left 2e5 / right 1e5, solved by the reference with SuperLU (245 s).  SURVEY's probe
+    values, the oracle's assembly, and the reference's x as the solution of the oracle's
+    system (a 125 000-unknown SuperLU solve is too slow for the CPU suite; the residual
+    and the rates are not)."""
+    name = "g18_config1_cubic50_spheres_and_cylinders"
+    g, m = golden(name), golden_meta[name]
+    assert (m["Np"], m["Nt"], m["nnz"]) == (125000, 367500, 830400)
+    assert np.isclose(m["rate_left"], 3.06977613e-07, rtol=1e-8)
+    assert np.isclose(g["g"].min(), 2.9e-15, rtol=0.02) and np.isclose(g["g"].max(), 7.3e-13, rtol=0.01)
+    net = oracle.cubic_network([50, 50, 50], spacing=1e-4)
+    Np = net["Np"]
+    bcv = np.full(Np, np.nan)
+    bcv[net["labels"]["left"]] = 2e5
+    bcv[net["labels"]["right"]] = 1e5
+    A, b, f = oracle.apply_bcs(oracle.build_A(net["conns"], g["g"], Np), Np, bcv, None)
+    M = oracle.to_csr(A, Np)
+    assert M.nnz == m["nnz"] and np.isclose(f, m["f"], rtol=1e-13)
+    assert np.linalg.norm(M @ g["x"] - b) <= 1e-13 * np.linalg.norm(b)
+    for side in ("left", "right"):
+        r = oracle.rate(net["conns"], g["g"], g["x"], pores=net["labels"][side])[0]
+        assert np.isclose(r, m["rate_" + side], rtol=1e-10)
+    assert np.isclose(m["rate_left"], -m["rate_right"], rtol=1e-10)
