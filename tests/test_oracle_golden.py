@@ -285,3 +285,41 @@ def test_config1_as_stated(golden, golden_meta):
         r = oracle.rate(net["conns"], g["g"], g["x"], pores=net["labels"][side])[0]
         assert np.isclose(r, m["rate_" + side], rtol=1e-10)
     assert np.isclose(m["rate_left"], -m["rate_right"], rtol=1e-10)
+
+
+def test_known_answers_of_the_reference_model_tests():
+    """Constants asserted by the reference's own model tests, on the oracle's restatements.
+    tests/unit/models/physics/HydraulicConductanceTest.py:8-37,
+    DiffusiveConductanceTest.py:8-36 (Cubic 5^3, size factors (0.123, 0.981, 0.551) or one
+    factor 0.896; viscosity 1e-5; diffusivity 1.3), SourceTermTest.py:41-89 (rate = S1 X + S2
+    at the linearisation point; the closed forms)."""
+    net = oracle.cubic_network([5, 5, 5])
+    conns, Np, Nt = net["conns"], net["Np"], net["Nt"]
+    sf3 = np.ones((Nt, 3)) * (0.123, 0.981, 0.551)
+    mu_p, mu_t = np.full(Np, 1e-5), np.full(Nt, 1e-5)
+    g = oracle.conduit_conductance("hydraulic", conns, mu_p, mu_t, sf3)
+    np.testing.assert_allclose(g.mean(), 9120.483231751232, rtol=1e-7)
+    g = oracle.conduit_conductance("hydraulic", conns, mu_p, mu_t, np.full(Nt, 0.896))
+    np.testing.assert_allclose(g.mean(), 89600.0, rtol=1e-7)
+    D_p, D_t = np.full(Np, 1.3), np.full(Nt, 1.3)
+    g = oracle.conduit_conductance("poisson", conns, D_p, D_t, sf3)
+    np.testing.assert_allclose(g.mean(), 0.091204832 * 1.3, rtol=1e-7)
+    g = oracle.conduit_conductance("poisson", conns, D_p, D_t, np.full(Nt, 0.896))
+    np.testing.assert_allclose(g.mean(), 0.896 * 1.3, rtol=1e-7)
+    # misc.from_neighbor_pores / polynomial on something one can do by hand
+    v = np.arange(Np, dtype=float)
+    c = conns[:5]
+    assert np.array_equal(oracle.from_neighbor_pores(c, v, "min"), c.min(axis=1))
+    assert np.array_equal(oracle.from_neighbor_pores(c, v, "max"), c.max(axis=1))
+    assert np.array_equal(oracle.from_neighbor_pores(c, v, "mean"), c.mean(axis=1))
+    np.testing.assert_allclose(oracle.polynomial([1.0, -2.0, 0.5], np.array([0.0, 2.0, 4.0])),
+                               [1.0, -1.0, 1.0])
+    # source terms
+    X = np.random.default_rng(0).uniform(0.1, 0.9, 50)
+    S1, S2, r = oracle.source_term("linear", X, dict(A1=0.5e-11, A2=1.5e-12))
+    np.testing.assert_allclose(r, 0.5e-11 * X + 1.5e-12, rtol=1e-15)
+    np.testing.assert_allclose(S1 * X + S2, r, rtol=1e-13)
+    S1, S2, r = oracle.source_term("power_law", X, dict(A1=0.5e-12, A2=2.5, A3=-1.4e-11))
+    np.testing.assert_allclose(r, 0.5e-12 * X ** 2.5 - 1.4e-11, rtol=1e-15)
+    np.testing.assert_allclose(S1 * X + S2, r, rtol=1e-12)
+    np.testing.assert_allclose(S1, 0.5e-12 * 2.5 * X ** 1.5, rtol=1e-14)
